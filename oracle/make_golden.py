@@ -1,0 +1,163 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference — TEST INFRASTRUCTURE.
+
+Runs only in the build container (needs /root/reference).  Imports pymbar from
+/root/reference through the numexpr stub in oracle/ref_shim, exercises
+the solver path on seeded inputs and stores the outputs.  Small cases store their u_kn; larger
+cases store only outputs plus a SHA-256 of the input bytes, and tests regenerate the input with
+oracle/testsystems.py (this script asserts that regeneration is bit-exact).
+
+    python oracle/make_golden.py
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(HERE, "ref_shim"))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, ROOT)
+os.environ["PYMBAR_DISABLE_JAX"] = "1"
+
+import pymbar  # noqa: E402  (the real reference)
+from pymbar import mbar_solvers as ref  # noqa: E402
+from pymbar import testsystems as ref_ts  # noqa: E402
+
+from oracle import testsystems as ots  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def ref_harmonic(O_k, K_k, N_k, seed):
+    tc = ref_ts.harmonic_oscillators.HarmonicOscillatorsTestCase(O_k=O_k, K_k=K_k)
+    _, u_kn, N_out, _ = tc.sample(N_k, mode="u_kn", seed=seed)
+    return u_kn, np.asarray(N_out)
+
+
+def ref_exponential(rates, N_k, seed):
+    tc = ref_ts.exponential_distributions.ExponentialTestCase(rates)
+    _, u_kn, N_out, _ = tc.sample(N_k, mode="u_kn", seed=seed)
+    return u_kn, np.asarray(N_out)
+
+
+def primitives(u_kn, N_k, f):
+    Nf = np.asarray(N_k, float)
+    sampled = Nf > 0
+    out = dict(
+        sci=ref.self_consistent_update(u_kn, Nf, f),
+        logW=ref.mbar_log_W_nk(u_kn, Nf, f),
+    )
+    # gradient / objective / hessian are only meaningful for sampled rows in the reference's solver
+    us, Ns, fs = u_kn[sampled], Nf[sampled], f[sampled]
+    out["grad"] = ref.mbar_gradient(us, Ns, fs)
+    out["obj"] = np.float64(ref.mbar_objective(us, Ns, fs))
+    out["hess"] = ref.mbar_hessian(us, Ns, fs)
+    return out
+
+
+def solve_all(u_kn, N_k):
+    res = {}
+    for name, proto in (
+        ("default", "default"),
+        ("robust", "robust"),
+        ("adaptive", (dict(method="adaptive", options=dict(min_sc_iter=0)),)),
+        ("adaptive_msi2", (dict(method="adaptive"),)),
+    ):
+        m = pymbar.MBAR(u_kn, N_k, solver_protocol=proto)
+        res[name] = np.array(m.f_k)
+    return res
+
+
+def case(name, u_kn, N_k, store_u, regen, rng):
+    K = u_kn.shape[0]
+    N_k = np.asarray(N_k, np.int64)
+    f_rand = rng.normal(scale=1.5, size=K)
+    f_rand -= f_rand[0]
+    data = dict(N_k=N_k, f_rand=f_rand, u_sha=np.array(sha(u_kn)), regen=np.array(repr(regen)))
+    if store_u:
+        data["u_kn"] = u_kn
+    for tag, f in (("zero", np.zeros(K)), ("rand", f_rand)):
+        for k, v in primitives(u_kn, N_k, f).items():
+            if k in ("logW", "hess") and not store_u:
+                # keep big fixtures out of git: store a few probes of the big outputs instead
+                if k == "hess":
+                    data[f"{tag}_hess_diag"] = np.diag(v).copy()
+                    data[f"{tag}_hess_row1"] = v[min(1, v.shape[0] - 1)].copy()
+                    data[f"{tag}_hess_fro"] = np.float64(np.linalg.norm(v))
+                else:
+                    data[f"{tag}_logW_colsum"] = v.sum(0)
+                    data[f"{tag}_logW_head"] = v[:4].copy()
+                continue
+            data[f"{tag}_{k}"] = v
+    for pname, fk in solve_all(u_kn, N_k).items():
+        data[f"fk_{pname}"] = fk
+    # adaptive trajectory from f=0 on sampled states (mbar_solvers.py:510-667), tol 1e-12
+    sampled = N_k > 0
+    us = ref.precondition_u_kn(u_kn[sampled], 1.0 * N_k[sampled], np.zeros(sampled.sum()))
+    r = ref.adaptive(us, 1.0 * N_k[sampled], np.zeros(sampled.sum()), tol=1e-12,
+                     options=dict(min_sc_iter=0))
+    data["adaptive_x"] = np.array(r["x"])
+    data["adaptive_success"] = np.array(bool(r["success"]))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **data)
+    print(f"{name}: K={K} N={u_kn.shape[1]} stored_u={store_u} "
+          f"fk_default[:4]={data['fk_default'][:4]}")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    rng = np.random.RandomState(1234)
+
+    # --- the reference's literal golden vector ---------------------------------------------
+    g = ots.GOLDEN_EXAMPLE
+    u_ref, N_ref = ref_harmonic(g["O_k"], g["K_k"], g["N_k"], g["seed"])
+    _, u_mine, _ = ots.harmonic_u_kn(g["O_k"], g["K_k"], g["N_k"], seed=g["seed"])
+    assert np.array_equal(u_ref, u_mine), "restated harmonic sampler is not bit-exact"
+    m = pymbar.MBAR(u_ref, N_ref, relative_tolerance=1.0e-10)
+    printed = np.array(g["f_k_printed"])
+    assert np.max(np.abs(m.f_k - printed)) < 5e-9, (m.f_k, printed)
+    case("golden_example", u_ref, N_ref, store_u=False,
+         regen=("harmonic", g["O_k"], g["K_k"], g["N_k"], g["seed"]), rng=rng)
+
+    # --- small cases, inputs stored ----------------------------------------------------------
+    O, Kk, Nk = np.linspace(1, 5, 8), np.linspace(1, 3, 8), [40] * 8
+    u, N = ref_harmonic(O, Kk, Nk, 1)
+    case("small_osc_8x40", u, N, True, ("harmonic", list(O), list(Kk), Nk, 1), rng)
+
+    rates, Nk = np.linspace(1, 3, 6), [50] * 6
+    u, N = ref_exponential(rates, Nk, 2)
+    case("small_exp_6x50", u, N, True, ("exponential", list(rates), Nk, 2), rng)
+
+    # tests/test_mbar.py:16 fixture shape: an empty state in the middle
+    O, Kk, Nk = [0, 1, 2, 3], [1, 2, 4, 8], [100, 50, 0, 80]
+    u, N = ref_harmonic(O, Kk, Nk, 3)
+    case("small_empty_state", u, N, True, ("harmonic", O, Kk, Nk, 3), rng)
+
+    # empty FIRST state (f_0 gauge applied after the all-state pass, mbar_solvers.py:1012-1015)
+    O, Kk, Nk = [0, 1, 2, 3, 4], [4, 4, 2, 2, 1], [0, 60, 60, 0, 60]
+    u, N = ref_harmonic(O, Kk, Nk, 4)
+    case("small_empty_first", u, N, True, ("harmonic", O, Kk, Nk, 4), rng)
+
+    # --- the shapes tests/test_mbar_solvers.py:25-41 uses; inputs regenerated -----------------
+    for (ks, ns, kind, seed) in ((50, 100, "osc", 10), (100, 100, "osc", 11),
+                                 (200, 50, "osc", 12), (200, 50, "exp", 13)):
+        if kind == "osc":
+            O, Kk = np.linspace(1, 5, ks), np.linspace(1, 3, ks)
+            u, N = ref_harmonic(O, Kk, [ns] * ks, seed)
+            u2, _ = ots.oscillators(ks, ns, seed=seed)
+        else:
+            rates = np.linspace(1, 3, ks)
+            u, N = ref_exponential(rates, [ns] * ks, seed)
+            u2, _ = ots.exponentials(ks, ns, seed=seed)
+        assert np.array_equal(u, u2), "restated sampler is not bit-exact"
+        case(f"{kind}_{ks}x{ns}", u, N, False, (kind, ks, ns, seed), rng)
+
+
+if __name__ == "__main__":
+    main()
