@@ -1,0 +1,170 @@
+/*
+ * mbar_b200.h — C ABI of libmbar_b200.so: the MBAR solve hot path on NVIDIA B200 (sm_100a).
+ *
+ * Drop-in boundary.  pymbar has no native FFI; its "operator API" for this path is the set of
+ * module-level functions in pymbar/mbar_solvers.py that pymbar.MBAR reaches by attribute lookup
+ * (mbar.py:413, :437, :455, :910).  Each entry point below names the reference function it stands
+ * in for (paths relative to /root/reference/pymbar/).  INTEGRATION.md shows the ctypes stub a
+ * pymbar maintainer would add beside the numpy/JAX switch at mbar_solvers.py:25-87.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is caller-owned HOST memory unless the name says "_dev";
+ *   - all functions return 0 (MBAR_B200_OK) or a negative mbar_b200_status; no exceptions, no
+ *     callbacks; mbar_b200_last_error() gives the message of the last failure on this thread;
+ *   - one context = one GPU = one contiguous slice [n0, n0+N_local) of the samples.  K-sized
+ *     state (N_k, f_k) is global and replicated.  With a communicator attached
+ *     (mbar_b200_comm_init) every reduction over samples is followed by one sum all-reduce of the
+ *     packed partials, so every rank returns identical K-vectors;
+ *   - u_kn is float64 [K, N] row-major on the host exactly as pymbar.MBAR holds it (mbar.py:243).
+ *     In HBM it is re-tiled to [N/32][K][32] and shifted per sample (see DESIGN.md "HBM layout");
+ *   - states with N_k == 0 are "unsampled": they never enter a denominator and only
+ *     mbar_b200_self_consistent_update / mbar_b200_log_W_nk produce values for them, exactly as in
+ *     the reference (mbar_solvers.py:1002-1012).
+ */
+#ifndef MBAR_B200_H
+#define MBAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBAR_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef struct mbar_b200_ctx mbar_b200_ctx;
+
+typedef enum mbar_b200_status {
+    MBAR_B200_OK = 0,
+    MBAR_B200_ERR_INVALID = -1,      /* bad argument (shape, NULL, K<1, ...)  -> ParameterError/ValueError */
+    MBAR_B200_ERR_CUDA = -2,         /* CUDA runtime failure                                             */
+    MBAR_B200_ERR_NO_DEVICE = -3,    /* no usable sm_100 GPU: there is NO CPU fallback                    */
+    MBAR_B200_ERR_NOT_READY = -4,    /* u_kn not uploaded / synthesised yet                               */
+    MBAR_B200_ERR_NAN = -5,          /* NaN found in u_kn at upload                                       */
+    MBAR_B200_ERR_RANGE = -6,        /* f_k + log N_k outside the supported +-1e6 range                   */
+    MBAR_B200_ERR_COMM = -7,         /* NCCL failure or libnccl not loadable                              */
+    MBAR_B200_ERR_SINGULAR = -8,     /* Newton system not positive definite (disconnected states)         */
+    MBAR_B200_ERR_NOMEM = -9
+} mbar_b200_status;
+
+/* Which kernel family a pass uses (mbar_b200_set_pass_kernel). AUTO = fused when it applies. */
+typedef enum mbar_b200_kernel {
+    MBAR_B200_KERNEL_AUTO = 0,
+    MBAR_B200_KERNEL_FUSED = 1,      /* TMA-pipelined persistent kernel, K <= 256                          */
+    MBAR_B200_KERNEL_GENERIC = 2     /* any K, log-domain for unsampled states                            */
+} mbar_b200_kernel;
+
+/* Result of a native solve (reference: the `results` dict of adaptive(), mbar_solvers.py:662-665). */
+typedef struct mbar_b200_solve_result {
+    int32_t success;          /* results["success"]                                                   */
+    int32_t iterations;       /* loop iterations executed                                             */
+    int32_t nr_iterations;    /* Newton-Raphson steps taken (nr_iter, mbar_solvers.py:620)            */
+    int32_t sci_iterations;   /* self-consistent steps taken (sci_iter, mbar_solvers.py:610)          */
+    int32_t passes;           /* full streaming passes over u_kn                                      */
+    int32_t hessian_passes;   /* of which with the K x K Hessian                                      */
+    double max_delta;         /* last relative change (mbar_solvers.py:631)                           */
+    double gnorm;             /* ||gradient||_2 at the returned f_k (mbar_solvers.py:938-940)          */
+    double device_ms;         /* CUDA-event time of the whole solve on this rank                      */
+} mbar_b200_solve_result;
+
+/* Synthetic-input family of SURVEY.md 8(d): harmonic oscillators, samples in block order. */
+typedef struct mbar_b200_synth {
+    uint64_t seed;            /* Philox-4x32-10 key; counter = GLOBAL sample index                     */
+    int64_t n_offset;         /* global index of this context's first sample                           */
+    int64_t N_global;         /* total samples over all ranks (defines the state of origin of n)       */
+    const double* O_k;        /* [K] oscillator centres                                                */
+    const double* k_k;        /* [K] spring constants (beta = 1)                                       */
+} mbar_b200_synth;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int mbar_b200_abi_version(void);
+const char* mbar_b200_last_error(void);
+int mbar_b200_device_count(int* count);
+/* Pinned host memory for zero-staging uploads/downloads (cudaHostAlloc / cudaFreeHost). */
+int mbar_b200_host_alloc(void** ptr, uint64_t bytes);
+int mbar_b200_host_free(void* ptr);
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* N_k: [K] global sample counts as float64 (validate_inputs casts to float, mbar_solvers.py:198). */
+int mbar_b200_create(mbar_b200_ctx** ctx, int device, int32_t K, int64_t N_local, const double* N_k);
+int mbar_b200_destroy(mbar_b200_ctx* ctx);
+int mbar_b200_get_shape(const mbar_b200_ctx* ctx, int32_t* K, int64_t* N_local);
+int mbar_b200_set_pass_kernel(mbar_b200_ctx* ctx, int kernel /* mbar_b200_kernel */);
+/* Counters since creation: kernel launches, streaming passes, bytes moved H2D / D2H. */
+int mbar_b200_get_counters(const mbar_b200_ctx* ctx, int64_t* launches, int64_t* passes,
+                           int64_t* h2d_bytes, int64_t* d2h_bytes);
+/* CUDA-event duration (ms) of the most recent pass kernel on the context's stream. */
+int mbar_b200_last_pass_ms(mbar_b200_ctx* ctx, double* ms);
+
+/* ---- data in / out -------------------------------------------------------------------------- */
+/* Replaces the host copies at mbar.py:243 and mbar_solvers.py:1003: u_host is [K, N_local]
+ * row-major with row stride `ld` (elements).  Pinned memory is DMA'd directly; pageable memory is
+ * staged through internal pinned buffers.  NaN anywhere -> MBAR_B200_ERR_NAN. */
+int mbar_b200_upload_u_kn(mbar_b200_ctx* ctx, const double* u_host, int64_t ld);
+/* Same, from a row-major DEVICE buffer on ctx's device (e.g. a torch tensor's data_ptr). */
+int mbar_b200_upload_u_kn_dev(mbar_b200_ctx* ctx, const double* u_dev, int64_t ld);
+/* Fill the context on device from the synthetic family (no host traffic). */
+int mbar_b200_synthesize(mbar_b200_ctx* ctx, const mbar_b200_synth* spec);
+/* Read back columns [n0, n0+n) of the ORIGINAL (unshifted) u_kn as [K, n] row-major, stride ld. */
+int mbar_b200_download_u_kn(mbar_b200_ctx* ctx, int64_t n0, int64_t n, double* u_host, int64_t ld);
+
+/* ---- the streaming pass and the reference primitives built on it ---------------------------- */
+/* One read of u_kn at f_k.  Outputs (any may be NULL):
+ *   S[K]    S_k = sum_n W_nk  (0 for unsampled states)
+ *   sumL    sum_n L_n,  L_n = log sum_k N_k exp(f_k - u_kn)   (mbar_solvers.py:238)
+ *   G[K*K]  G = W^T W row-major (0 rows/cols for unsampled states); costs the Hessian pass.
+ * With a communicator the outputs are the all-reduced global sums. */
+int mbar_b200_pass(mbar_b200_ctx* ctx, const double* f_k, double* S, double* sumL, double* G);
+
+/* self_consistent_update(u_kn, N_k, f_k)  — mbar_solvers.py:206-257, Eq. C3, ALL states. */
+int mbar_b200_self_consistent_update(mbar_b200_ctx* ctx, const double* f_k, double* f_out);
+/* mbar_gradient — mbar_solvers.py:260-292, Eq. C6.  Unsampled states get 0 (-N_k * ...). */
+int mbar_b200_gradient(mbar_b200_ctx* ctx, const double* f_k, double* g_out);
+/* mbar_objective_and_gradient — mbar_solvers.py:341-392 (g_out may be NULL = mbar_objective). */
+int mbar_b200_objective_and_gradient(mbar_b200_ctx* ctx, const double* f_k, double* obj_out,
+                                     double* g_out);
+/* mbar_hessian — mbar_solvers.py:395-436, Eq. C9, [K, K] row-major. */
+int mbar_b200_hessian(mbar_b200_ctx* ctx, const double* f_k, double* H_out);
+/* mbar_log_W_nk — mbar_solvers.py:439-473: [N_local, K] row-major (note: transposed w.r.t. u_kn),
+ * row stride ld_out elements; exponentiate != 0 gives mbar_W_nk (mbar_solvers.py:476-507). */
+int mbar_b200_log_W_nk(mbar_b200_ctx* ctx, const double* f_k, double* logW_host, int64_t ld_out,
+                       int exponentiate);
+/* Per-sample log denominators L_n [N_local] (the logsumexp at mbar_solvers.py:238). */
+int mbar_b200_log_denominator(mbar_b200_ctx* ctx, const double* f_k, double* L_host);
+
+/* ---- native solver loops (no Python between iterations) ------------------------------------- */
+/* Plain self-consistent iteration f <- f - log S(f), gauge f[first sampled] = 0 each step, until
+ * max |delta f / f| < tol (the convergence rule of mbar_solvers.py:627-640) or maxiter. */
+int mbar_b200_solve_sci(mbar_b200_ctx* ctx, double* f_inout, double tol, int32_t maxiter,
+                        mbar_b200_solve_result* result);
+/* adaptive() — mbar_solvers.py:510-667: Newton vs self-consistent step by gradient norm.
+ * f_inout covers all K states; unsampled states are carried through untouched. */
+int mbar_b200_solve_adaptive(mbar_b200_ctx* ctx, double* f_inout, double tol, int32_t maxiter,
+                             int32_t min_sc_iter, double gamma, mbar_b200_solve_result* result);
+/* Run exactly `iters` self-consistent passes back to back with no host round trip (bench). */
+int mbar_b200_sci_iterate(mbar_b200_ctx* ctx, double* f_inout, int32_t iters);
+
+/* ---- one-shot, host-buffer entry (what a binding without residency would call) --------------- */
+/* self_consistent_update on host buffers: upload u_kn, one pass, f_out — copies inside the call. */
+int mbar_b200_self_consistent_update_host(int device, int32_t K, int64_t N, const double* u_host,
+                                          int64_t ld, const double* N_k, const double* f_k,
+                                          double* f_out);
+
+/* ---- multi-GPU: samples sharded over ranks, one all-reduce per pass -------------------------- */
+#define MBAR_B200_UNIQUE_ID_BYTES 128
+int mbar_b200_comm_unique_id(void* id_out /* [128] */);
+int mbar_b200_comm_init(mbar_b200_ctx* ctx, int32_t nranks, int32_t rank, const void* unique_id);
+int mbar_b200_comm_destroy(mbar_b200_ctx* ctx);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBAR_B200_H */

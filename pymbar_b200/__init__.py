@@ -1,0 +1,55 @@
+"""pymbar_b200 — the MBAR solve hot path of pymbar on NVIDIA B200 (sm_100a).
+
+Public surface:
+  * :mod:`pymbar_b200.mbar_solvers` — same names/signatures as ``pymbar.mbar_solvers``;
+  * :class:`pymbar_b200.DeviceProblem` — explicit residency handle (one GPU, one shard of samples);
+  * :func:`pymbar_b200.install` — rebind ``pymbar.mbar_solvers`` so unmodified ``pymbar.MBAR`` uses it.
+
+Everything numerical runs in libmbar_b200.so (C ABI in include/mbar_b200.h).  No CPU fallback.
+"""
+from . import _lib
+from .problem import DeviceProblem, PinnedArray
+from .utils import ParameterError
+
+__all__ = ["DeviceProblem", "PinnedArray", "ParameterError", "install", "uninstall", "mbar_solvers"]
+
+_SAVED = {}
+_PATCHED = (
+    "self_consistent_update", "mbar_gradient", "mbar_objective", "mbar_objective_and_gradient",
+    "mbar_hessian", "mbar_log_W_nk", "mbar_W_nk", "precondition_u_kn", "adaptive",
+    "solve_mbar_once", "solve_mbar", "solve_mbar_for_all_states",
+    "jax_self_consistent_update", "jax_mbar_gradient", "jax_mbar_objective",
+    "jax_mbar_objective_and_gradient", "jax_mbar_hessian", "jax_mbar_log_W_nk", "jax_mbar_W_nk",
+    "jax_precondition_u_kn",
+)
+
+
+def install(target=None):
+    """Route ``pymbar.mbar_solvers`` (or `target`, a module object) through the B200 backend.
+
+    pymbar looks its solver entry points up as module attributes at call time (mbar.py:413, :437,
+    :455, :910), so rebinding them is the whole integration; nothing in pymbar is edited."""
+    from . import mbar_solvers as backend
+
+    _lib.load()
+    if target is None:
+        import pymbar.mbar_solvers as target  # noqa: F811
+    for name in _PATCHED:
+        if hasattr(target, name) and (target, name) not in _SAVED:
+            _SAVED[(target, name)] = getattr(target, name)
+        setattr(target, name, getattr(backend, name))
+    return target
+
+
+def uninstall():
+    for (target, name), fn in list(_SAVED.items()):
+        setattr(target, name, fn)
+        del _SAVED[(target, name)]
+
+
+def __getattr__(name):
+    if name == "mbar_solvers":
+        import importlib
+
+        return importlib.import_module(".mbar_solvers", __name__)
+    raise AttributeError(name)

@@ -1,0 +1,547 @@
+// Context, HBM layout and data movement for libmbar_b200.so.
+//
+// HBM layout ("tile-major"): u_kn [K, N] row-major on the host (mbar.py:243) is stored on device as
+//   d_u[tile][k][lane],  tile = n / 32, lane = n % 32,
+// so the K x 32 block of one group of 32 samples is ONE contiguous K*256-byte extent: a streaming
+// pass is a sequence of large contiguous bulk copies, and each warp lane owns one sample.
+// At upload every sample is shifted by x_n = min over SAMPLED states of u_kn (the first step of
+// precondition_u_kn, mbar_solvers.py:705) and clamped to <= 1e6; gradient, Hessian, weights and
+// the self-consistent update are invariant under a per-sample shift, the
+// objective changes by the constant sum_n x_n which the context carries.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "internal.cuh"
+
+namespace mbar {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------
+// Re-tile + shift kernel.  One CTA (8 warps) per tile; lane = sample, warp w owns rows w, w+8, ...
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) retile_kernel(const double* __restrict__ src, int64_t ld,
+                                                     int K, int64_t tile0, int64_t validCols,
+                                                     const unsigned long long* __restrict__ rowmask,
+                                                     double* __restrict__ dst,
+                                                     double* __restrict__ xshift,
+                                                     int* __restrict__ flags) {
+    __shared__ double s_min[8][TILE_N];
+    __shared__ int s_bad[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tileLocal = blockIdx.x;
+    const int64_t col = tileLocal * TILE_N + lane;
+    const bool valid = col < validCols;
+    const double* colp = src + col;
+
+    double mn = INFINITY;
+    int bad = 0;
+    for (int k = warp; k < K; k += 8) {
+        double v = valid ? colp[(int64_t)k * ld] : 0.0;
+        if (v != v) bad = 1;
+        const bool act = (rowmask[k >> 6] >> (k & 63)) & 1ull;
+        if (act) mn = fmin(mn, v);
+    }
+    s_min[warp][lane] = mn;
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) s_bad[warp] = bad;
+    __syncthreads();
+    double x = s_min[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) x = fmin(x, s_min[w][lane]);
+    int anyBad = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) anyBad |= s_bad[w];
+    // a sample whose sampled-state energies are all +inf (or contain -inf) has no finite weight
+    const bool finiteShift = isfinite(x);
+    if (valid && !finiteShift) anyBad |= 2;
+    if (!valid || !finiteShift) x = 0.0;
+
+    double* out = dst + (tile0 + tileLocal) * (int64_t)K * TILE_N + lane;
+    for (int k = warp; k < K; k += 8) {
+        double v = valid ? colp[(int64_t)k * ld] : 0.0;
+        v = fmin(v - x, U_CLAMP);
+        out[(int64_t)k * TILE_N] = valid ? v : 0.0;
+    }
+    if (warp == 0) xshift[(tile0 + tileLocal) * TILE_N + lane] = x;
+    if (anyBad && threadIdx.x == 0) atomicOr(&flags[0], anyBad);
+}
+
+int retile_chunk(mbar_b200_ctx* ctx, const double* d_rowmajor, int64_t ldCols, int64_t tile0,
+                 int64_t nTilesChunk, int64_t validCols, cudaStream_t s) {
+    if (nTilesChunk <= 0) return MBAR_B200_OK;
+    retile_kernel<<<(unsigned)nTilesChunk, 256, 0, s>>>(d_rowmajor, ldCols, ctx->K, tile0, validCols,
+                                                       ctx->d_rowmask, ctx->d_u, ctx->d_xshift,
+                                                       ctx->d_flag);
+    ctx->launches++;
+    MBAR_CUDA(cudaGetLastError());
+    return MBAR_B200_OK;
+}
+
+// Inverse of the re-tile for verification: original-frame u = u' + x_n, row-major [K, n].
+__global__ void __launch_bounds__(256) untile_kernel(const double* __restrict__ u,
+                                                     const double* __restrict__ xshift, int K,
+                                                     int64_t n0, int64_t n, double* __restrict__ dst,
+                                                     int64_t ld) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t j = (int64_t)blockIdx.x * TILE_N + lane;  // column in the output
+    if (j >= n) return;
+    const int64_t g = n0 + j;
+    const int64_t tile = g / TILE_N;
+    const int l = (int)(g % TILE_N);
+    const double x = xshift[g];
+    for (int k = warp; k < K; k += 8)
+        dst[(int64_t)k * ld + j] = u[(tile * K + k) * TILE_N + l] + x;
+}
+
+int launch_untile(mbar_b200_ctx* ctx, int64_t n0, int64_t n, double* d_dst, int64_t ld) {
+    const unsigned grid = (unsigned)((n + TILE_N - 1) / TILE_N);
+    untile_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_u, ctx->d_xshift, ctx->K, n0, n, d_dst, ld);
+    ctx->launches++;
+    MBAR_CUDA(cudaGetLastError());
+    return MBAR_B200_OK;
+}
+
+// sum of the per-sample shifts (valid samples only) -> one double
+__global__ void __launch_bounds__(256) sumx_kernel(const double* __restrict__ x, int64_t N,
+                                                   double* __restrict__ partial) {
+    __shared__ double s[8];
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+         i += (int64_t)gridDim.x * blockDim.x)
+        acc += x[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s[w];
+        partial[blockIdx.x] = t;
+    }
+}
+
+int reduce_sumx(mbar_b200_ctx* ctx) {
+    const int grid = 256;
+    sumx_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_xshift, ctx->N, ctx->d_scratch);
+    ctx->launches++;
+    MBAR_CUDA(cudaGetLastError());
+    std::vector<double> h(grid);
+    MBAR_CUDA(cudaMemcpyAsync(h.data(), ctx->d_scratch, grid * sizeof(double), cudaMemcpyDeviceToHost,
+                              ctx->stream));
+    MBAR_CUDA(cudaStreamSynchronize(ctx->stream));
+    double t = 0.0;
+    for (double v : h) t += v;
+    ctx->sumX = t;
+    return MBAR_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Synthetic harmonic-oscillator inputs generated in place: Philox-4x32-10 keyed by
+// the seed with the GLOBAL sample index as counter, so every shard regenerates exactly its slice.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void __launch_bounds__(256) synth_kernel(int K, int64_t N, int64_t nOffset, uint64_t seed,
+                                                    const double* __restrict__ O_k,
+                                                    const double* __restrict__ k_k,
+                                                    const double* __restrict__ cumN,  // [K+1]
+                                                    const unsigned long long* __restrict__ rowmask,
+                                                    double* __restrict__ dst,
+                                                    double* __restrict__ xshift) {
+    __shared__ double s_min[8][TILE_N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = blockIdx.x;
+    const int64_t nl = tile * TILE_N + lane;
+    const bool valid = nl < N;
+    const int64_t g = nOffset + nl;
+    // state of origin: largest s with cumN[s] <= g
+    int lo = 0, hi = K;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (cumN[mid] <= (double)g) lo = mid; else hi = mid;
+    }
+    uint32_t r[4];
+    philox4x32_10((uint32_t)g, (uint32_t)((uint64_t)g >> 32), 0u, 0u, (uint32_t)seed,
+                  (uint32_t)(seed >> 32), r);
+    const double u1 = ((double)((((uint64_t)r[0] << 32) | r[1]) >> 11) + 0.5) * 0x1.0p-53;
+    const double u2 = ((double)((((uint64_t)r[2] << 32) | r[3]) >> 11) + 0.5) * 0x1.0p-53;
+    const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    const double x = O_k[lo] + z * rsqrt(k_k[lo]);
+
+    double mn = INFINITY;
+    for (int k = warp; k < K; k += 8) {
+        const bool act = (rowmask[k >> 6] >> (k & 63)) & 1ull;
+        const double d = x - O_k[k];
+        if (act) mn = fmin(mn, 0.5 * k_k[k] * d * d);
+    }
+    s_min[warp][lane] = mn;
+    __syncthreads();
+    double sh = s_min[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) sh = fmin(sh, s_min[w][lane]);
+    if (!valid) sh = 0.0;
+    double* out = dst + tile * (int64_t)K * TILE_N + lane;
+    for (int k = warp; k < K; k += 8) {
+        const double d = x - O_k[k];
+        const double v = fmin(0.5 * k_k[k] * d * d - sh, U_CLAMP);
+        out[(int64_t)k * TILE_N] = valid ? v : 0.0;
+    }
+    if (warp == 0) xshift[nl] = sh;
+}
+
+int launch_synth(mbar_b200_ctx* ctx, const mbar_b200_synth* spec) {
+    const int K = ctx->K;
+    std::vector<double> h(3 * (size_t)K + 1);
+    for (int k = 0; k < K; ++k) {
+        h[k] = spec->O_k[k];
+        h[K + k] = spec->k_k[k];
+        MBAR_REQUIRE(spec->k_k[k] > 0, MBAR_B200_ERR_INVALID, "synth: k_k[%d] must be > 0", k);
+    }
+    double c = 0.0;
+    for (int k = 0; k <= K; ++k) {
+        h[2 * K + k] = c;
+        if (k < K) c += ctx->h_Nk[k];
+    }
+    double* d = ctx->d_scratch;  // >= K*K + 4K doubles
+    MBAR_CUDA(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice,
+                              ctx->stream));
+    synth_kernel<<<(unsigned)ctx->nTiles, 256, 0, ctx->stream>>>(
+        K, ctx->N, spec->n_offset, spec->seed, d, d + K, d + 2 * K, ctx->d_rowmask, ctx->d_u,
+        ctx->d_xshift);
+    ctx->launches++;
+    MBAR_CUDA(cudaGetLastError());
+    MBAR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MBAR_B200_OK;
+}
+
+}  // namespace mbar
+
+using namespace mbar;
+
+// ------------------------------------------------------------------------------------------
+// C ABI: library + context + data movement
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int mbar_b200_abi_version(void) { return MBAR_B200_ABI_VERSION; }
+const char* mbar_b200_last_error(void) { return g_err; }
+
+int mbar_b200_device_count(int* count) {
+    MBAR_REQUIRE(count, MBAR_B200_ERR_INVALID, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *count = n;
+    return MBAR_B200_OK;
+}
+
+int mbar_b200_host_alloc(void** ptr, uint64_t bytes) {
+    MBAR_REQUIRE(ptr, MBAR_B200_ERR_INVALID, "ptr is NULL");
+    MBAR_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return MBAR_B200_OK;
+}
+int mbar_b200_host_free(void* ptr) {
+    if (ptr) MBAR_CUDA(cudaFreeHost(ptr));
+    return MBAR_B200_OK;
+}
+
+int mbar_b200_create(mbar_b200_ctx** out, int device, int32_t K, int64_t N_local, const double* N_k) {
+    MBAR_REQUIRE(out && N_k, MBAR_B200_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    MBAR_REQUIRE(K >= 1 && K <= 8192, MBAR_B200_ERR_INVALID, "K=%d outside [1, 8192]", K);
+    MBAR_REQUIRE(N_local >= 1, MBAR_B200_ERR_INVALID, "N_local=%lld must be >= 1", (long long)N_local);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device visible: libmbar_b200 has no CPU fallback");
+        return MBAR_B200_ERR_NO_DEVICE;
+    }
+    MBAR_REQUIRE(device >= 0 && device < ndev, MBAR_B200_ERR_INVALID, "device %d of %d", device, ndev);
+    MBAR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MBAR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                  prop.major, prop.minor);
+        return MBAR_B200_ERR_NO_DEVICE;
+    }
+    mbar_b200_ctx* c = new mbar_b200_ctx();
+    c->device = device;
+    c->K = K;
+    c->N = N_local;
+    c->nTiles = (N_local + TILE_N - 1) / TILE_N;
+    c->smCount = prop.multiProcessorCount;
+    c->h_Nk.assign(N_k, N_k + K);
+    c->h_logNk.resize(K);
+    std::vector<unsigned long long> mask((K + 63) / 64, 0ull);
+    for (int k = 0; k < K; ++k) {
+        if (!(N_k[k] >= 0.0)) {
+            delete c;
+            set_error("N_k[%d]=%g is negative or NaN", k, N_k[k]);
+            return MBAR_B200_ERR_INVALID;
+        }
+        c->N_total_states += N_k[k];
+        if (N_k[k] > 0) {
+            c->active.push_back(k);
+            mask[k >> 6] |= 1ull << (k & 63);
+            c->h_logNk[k] = std::log(N_k[k]);
+        } else {
+            c->h_logNk[k] = -INFINITY;
+        }
+    }
+    if (c->active.empty()) {
+        delete c;
+        set_error("all N_k are zero");
+        return MBAR_B200_ERR_INVALID;
+    }
+    c->firstActive = c->active[0];
+
+    const size_t uBytes = (size_t)c->nTiles * K * TILE_N * sizeof(double);
+    const size_t nPad = (size_t)c->nTiles * TILE_N;
+    const PassLayout lay{K};
+#define ALLOC(p, bytes)                                                        \
+    do {                                                                       \
+        cudaError_t e = cudaMalloc((void**)&(p), (bytes));                     \
+        if (e != cudaSuccess) {                                                \
+            set_error("cudaMalloc(%zu bytes) failed: %s", (size_t)(bytes), cudaGetErrorString(e)); \
+            mbar_b200_destroy(c);                                              \
+            return MBAR_B200_ERR_NOMEM;                                        \
+        }                                                                      \
+    } while (0)
+    ALLOC(c->d_u, uBytes);
+    ALLOC(c->d_xshift, nPad * sizeof(double));
+    ALLOC(c->d_c, 4 * (size_t)K * sizeof(double));
+    ALLOC(c->d_Nk, (size_t)K * sizeof(double));
+    ALLOC(c->d_rowmask, mask.size() * sizeof(unsigned long long));
+    ALLOC(c->d_partial, (size_t)MAX_GRID * (3 * (size_t)K + 2) * sizeof(double));
+    ALLOC(c->d_out, (size_t)lay.size(true) * sizeof(double));
+    ALLOC(c->d_ticket, 4 * sizeof(unsigned int));
+    ALLOC(c->d_flag, 4 * sizeof(int));
+    ALLOC(c->d_f, 8 * (size_t)K * sizeof(double));
+    ALLOC(c->d_scratch, ((size_t)K * K + 4 * (size_t)K + 1024) * sizeof(double));
+#undef ALLOC
+    MBAR_CUDA(cudaHostAlloc((void**)&c->h_out, (size_t)lay.size(true) * sizeof(double), cudaHostAllocDefault));
+    MBAR_CUDA(cudaHostAlloc((void**)&c->h_f, 8 * (size_t)K * sizeof(double), cudaHostAllocDefault));
+    MBAR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    MBAR_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+    MBAR_CUDA(cudaEventCreate(&c->evA));
+    MBAR_CUDA(cudaEventCreate(&c->evB));
+    MBAR_CUDA(cudaEventCreateWithFlags(&c->evCopy[0], cudaEventDisableTiming));
+    MBAR_CUDA(cudaEventCreateWithFlags(&c->evCopy[1], cudaEventDisableTiming));
+    MBAR_CUDA(cudaMemcpy(c->d_Nk, N_k, (size_t)K * sizeof(double), cudaMemcpyHostToDevice));
+    MBAR_CUDA(cudaMemcpy(c->d_rowmask, mask.data(), mask.size() * sizeof(unsigned long long),
+                         cudaMemcpyHostToDevice));
+    MBAR_CUDA(cudaMemset(c->d_ticket, 0, 4 * sizeof(unsigned int)));
+    MBAR_CUDA(cudaMemset(c->d_flag, 0, 4 * sizeof(int)));
+    *out = c;
+    return MBAR_B200_OK;
+}
+
+int mbar_b200_destroy(mbar_b200_ctx* c) {
+    if (!c) return MBAR_B200_OK;
+    cudaSetDevice(c->device);
+    if (c->comm) mbar_b200_comm_destroy(c);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_u); cudaFree(c->d_xshift); cudaFree(c->d_c); cudaFree(c->d_Nk);
+    cudaFree(c->d_rowmask); cudaFree(c->d_partial); cudaFree(c->d_out); cudaFree(c->d_L);
+    cudaFree(c->d_W); cudaFree(c->d_ticket); cudaFree(c->d_flag); cudaFree(c->d_f);
+    cudaFree(c->d_scratch);
+    for (int i = 0; i < 2; ++i) {
+        if (c->stage_pinned[i]) cudaFreeHost(c->stage_pinned[i]);
+        cudaFree(c->stage_dev[i]);
+        if (c->evCopy[i]) cudaEventDestroy(c->evCopy[i]);
+    }
+    if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->h_f) cudaFreeHost(c->h_f);
+    if (c->evA) cudaEventDestroy(c->evA);
+    if (c->evB) cudaEventDestroy(c->evB);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copyStream) cudaStreamDestroy(c->copyStream);
+    cudaGetLastError();
+    delete c;
+    return MBAR_B200_OK;
+}
+
+int mbar_b200_get_shape(const mbar_b200_ctx* c, int32_t* K, int64_t* N_local) {
+    MBAR_REQUIRE(c, MBAR_B200_ERR_INVALID, "ctx is NULL");
+    if (K) *K = c->K;
+    if (N_local) *N_local = c->N;
+    return MBAR_B200_OK;
+}
+
+int mbar_b200_set_pass_kernel(mbar_b200_ctx* c, int kernel) {
+    MBAR_REQUIRE(c, MBAR_B200_ERR_INVALID, "ctx is NULL");
+    MBAR_REQUIRE(kernel >= 0 && kernel <= 2, MBAR_B200_ERR_INVALID, "kernel=%d", kernel);
+    c->kernelChoice = kernel;
+    return MBAR_B200_OK;
+}
+
+int mbar_b200_get_counters(const mbar_b200_ctx* c, int64_t* launches, int64_t* passes,
+                           int64_t* h2d, int64_t* d2h) {
+    MBAR_REQUIRE(c, MBAR_B200_ERR_INVALID, "ctx is NULL");
+    if (launches) *launches = c->launches;
+    if (passes) *passes = c->passes;
+    if (h2d) *h2d = c->h2dBytes;
+    if (d2h) *d2h = c->d2hBytes;
+    return MBAR_B200_OK;
+}
+
+int mbar_b200_last_pass_ms(mbar_b200_ctx* c, double* ms) {
+    MBAR_REQUIRE(c && ms, MBAR_B200_ERR_INVALID, "NULL argument");
+    *ms = c->lastPassMs;
+    return MBAR_B200_OK;
+}
+
+static int ensure_staging(mbar_b200_ctx* c, bool needPinned) {
+    if (c->stageCols == 0) {
+        // ~64 MiB per staging buffer, whole tiles
+        int64_t cols = (64ll << 20) / (8ll * c->K);
+        cols = (cols / TILE_N) * TILE_N;
+        if (cols < TILE_N) cols = TILE_N;
+        const int64_t padN = c->nTiles * TILE_N;
+        if (cols > padN) cols = padN;
+        c->stageCols = cols;
+    }
+    const size_t bytes = (size_t)c->stageCols * c->K * sizeof(double);
+    for (int i = 0; i < 2; ++i) {
+        if (!c->stage_dev[i]) MBAR_CUDA(cudaMalloc((void**)&c->stage_dev[i], bytes));
+        if (needPinned && !c->stage_pinned[i])
+            MBAR_CUDA(cudaHostAlloc((void**)&c->stage_pinned[i], bytes, cudaHostAllocDefault));
+    }
+    return MBAR_B200_OK;
+}
+
+static int finish_upload(mbar_b200_ctx* c) {
+    int flags[4];
+    MBAR_CUDA(cudaStreamSynchronize(c->copyStream));
+    MBAR_CUDA(cudaStreamSynchronize(c->stream));
+    MBAR_CUDA(cudaMemcpy(flags, c->d_flag, sizeof(flags), cudaMemcpyDeviceToHost));
+    if (flags[0]) {
+        MBAR_CUDA(cudaMemset(c->d_flag, 0, 4 * sizeof(int)));
+        c->ready = false;
+        set_error(flags[0] & 1 ? "u_kn contains NaN"
+                               : "a sample has no finite energy in any sampled state");
+        return MBAR_B200_ERR_NAN;
+    }
+    MBAR_TRY(reduce_sumx(c));
+    c->ready = true;
+    return MBAR_B200_OK;
+}
+
+int mbar_b200_upload_u_kn(mbar_b200_ctx* c, const double* u_host, int64_t ld) {
+    MBAR_REQUIRE(c && u_host, MBAR_B200_ERR_INVALID, "NULL argument");
+    MBAR_REQUIRE(ld >= c->N, MBAR_B200_ERR_INVALID, "ld=%lld < N_local=%lld", (long long)ld,
+                 (long long)c->N);
+    MBAR_CUDA(cudaSetDevice(c->device));
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, u_host) == cudaSuccess)
+        pinned = (attr.type == cudaMemoryTypeHost);
+    else
+        cudaGetLastError();
+    MBAR_TRY(ensure_staging(c, !pinned));
+    const int K = c->K;
+    const int64_t cols = c->stageCols;
+    int buf = 0;
+    // double-buffered: copy chunk i+1 (copyStream) while chunk i is re-tiled (stream)
+    for (int64_t n0 = 0; n0 < c->N; n0 += cols, buf ^= 1) {
+        const int64_t w = (c->N - n0 < cols) ? (c->N - n0) : cols;
+        // the re-tile that last read stage_dev[buf] must be done before we overwrite it
+        MBAR_CUDA(cudaStreamWaitEvent(c->copyStream, c->evCopy[buf], 0));
+        const double* src = u_host + n0;
+        int64_t srcLd = ld;
+        if (!pinned) {
+            // pageable memory: pack the chunk into the pinned staging buffer on the CPU
+            MBAR_CUDA(cudaEventSynchronize(c->evCopy[buf]));
+            double* p = c->stage_pinned[buf];
+            for (int k = 0; k < K; ++k)
+                std::memcpy(p + (size_t)k * w, u_host + (size_t)k * ld + n0, (size_t)w * sizeof(double));
+            src = p;
+            srcLd = w;
+        }
+        MBAR_CUDA(cudaMemcpy2DAsync(c->stage_dev[buf], (size_t)cols * sizeof(double), src,
+                                    (size_t)srcLd * sizeof(double), (size_t)w * sizeof(double), K,
+                                    cudaMemcpyHostToDevice, c->copyStream));
+        c->h2dBytes += (int64_t)w * K * 8;
+        cudaEvent_t copied;
+        MBAR_CUDA(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+        MBAR_CUDA(cudaEventRecord(copied, c->copyStream));
+        MBAR_CUDA(cudaStreamWaitEvent(c->stream, copied, 0));
+        MBAR_CUDA(cudaEventDestroy(copied));
+        const int64_t nT = (w + TILE_N - 1) / TILE_N;
+        MBAR_TRY(retile_chunk(c, c->stage_dev[buf], cols, n0 / TILE_N, nT, w, c->stream));
+        MBAR_CUDA(cudaEventRecord(c->evCopy[buf], c->stream));
+    }
+    return finish_upload(c);
+}
+
+int mbar_b200_upload_u_kn_dev(mbar_b200_ctx* c, const double* u_dev, int64_t ld) {
+    MBAR_REQUIRE(c && u_dev, MBAR_B200_ERR_INVALID, "NULL argument");
+    MBAR_REQUIRE(ld >= c->N, MBAR_B200_ERR_INVALID, "ld=%lld < N_local", (long long)ld);
+    MBAR_CUDA(cudaSetDevice(c->device));
+    MBAR_TRY(retile_chunk(c, u_dev, ld, 0, c->nTiles, c->N, c->stream));
+    return finish_upload(c);
+}
+
+int mbar_b200_synthesize(mbar_b200_ctx* c, const mbar_b200_synth* spec) {
+    MBAR_REQUIRE(c && spec && spec->O_k && spec->k_k, MBAR_B200_ERR_INVALID, "NULL argument");
+    MBAR_CUDA(cudaSetDevice(c->device));
+    MBAR_TRY(launch_synth(c, spec));
+    MBAR_TRY(reduce_sumx(c));
+    c->ready = true;
+    return MBAR_B200_OK;
+}
+
+int mbar_b200_download_u_kn(mbar_b200_ctx* c, int64_t n0, int64_t n, double* u_host, int64_t ld) {
+    MBAR_REQUIRE(c && u_host, MBAR_B200_ERR_INVALID, "NULL argument");
+    MBAR_REQUIRE(c->ready, MBAR_B200_ERR_NOT_READY, "u_kn not uploaded");
+    MBAR_REQUIRE(n0 >= 0 && n >= 1 && n0 + n <= c->N && ld >= n, MBAR_B200_ERR_INVALID,
+                 "bad slice [%lld, +%lld) ld=%lld", (long long)n0, (long long)n, (long long)ld);
+    MBAR_CUDA(cudaSetDevice(c->device));
+    // chunked through a device row-major buffer
+    const int64_t maxCols = (32ll << 20) / (8ll * c->K) / TILE_N * TILE_N + TILE_N;
+    double* d_tmp = nullptr;
+    const int64_t cols = n < maxCols ? n : maxCols;
+    MBAR_CUDA(cudaMalloc((void**)&d_tmp, (size_t)cols * c->K * sizeof(double)));
+    int rc = MBAR_B200_OK;
+    for (int64_t j = 0; j < n && rc == MBAR_B200_OK; j += cols) {
+        const int64_t w = (n - j < cols) ? (n - j) : cols;
+        rc = launch_untile(c, n0 + j, w, d_tmp, cols);
+        if (rc != MBAR_B200_OK) break;
+        cudaError_t e = cudaMemcpy2DAsync(u_host + j, (size_t)ld * sizeof(double), d_tmp,
+                                          (size_t)cols * sizeof(double), (size_t)w * sizeof(double),
+                                          c->K, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            set_error("download failed: %s", cudaGetErrorString(e));
+            rc = MBAR_B200_ERR_CUDA;
+        }
+        c->d2hBytes += (int64_t)w * c->K * 8;
+    }
+    cudaFree(d_tmp);
+    return rc;
+}
+
+}  // extern "C"

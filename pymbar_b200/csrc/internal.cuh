@@ -1,0 +1,220 @@
+// Shared internals of libmbar_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+#include "../../include/mbar_b200.h"
+#include "exp_tables.h"
+
+namespace mbar {
+
+constexpr int TILE_N = 32;              // samples per tile (one warp lane each)
+constexpr double U_CLAMP = 1.0e6;       // shifted energies are clamped to [.., 1e6] at upload
+constexpr double C_RANGE = 1.0e6;       // |f_k + log N_k| must stay below this
+constexpr double FUSED_SPREAD = 1200.0; // fused kernel needs max(c) - min(c) below this
+constexpr int MAX_GRID = 148 * 4;
+
+void set_error(const char* fmt, ...);
+#define MBAR_CUDA(call)                                                                     \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            mbar::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,            \
+                            cudaGetErrorString(e__));                                       \
+            return MBAR_B200_ERR_CUDA;                                                      \
+        }                                                                                   \
+    } while (0)
+#define MBAR_REQUIRE(cond, status, ...)                                                     \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            mbar::set_error(__VA_ARGS__);                                                   \
+            return (status);                                                                \
+        }                                                                                   \
+    } while (0)
+#define MBAR_TRY(call)                                                                      \
+    do {                                                                                    \
+        int s__ = (call);                                                                   \
+        if (s__ != MBAR_B200_OK) return s__;                                                \
+    } while (0)
+
+// Packed per-pass output on device / pinned host:  [0..K) S_k, [K] sumL, [K+1] flag (as double),
+// [K+2 .. K+2+K) log-domain S for unsampled states (generic kernel), then K*K G when requested.
+struct PassLayout {
+    int K;
+    __host__ __device__ int S() const { return 0; }
+    __host__ __device__ int sumL() const { return K; }
+    __host__ __device__ int flag() const { return K + 1; }
+    __host__ __device__ int logS() const { return K + 2; }
+    __host__ __device__ int G() const { return 2 * K + 2; }
+    __host__ __device__ int size(bool withG) const { return 2 * K + 2 + (withG ? K * K : 0); }
+};
+
+}  // namespace mbar
+
+struct mbar_b200_ctx {
+    int device = 0;
+    int K = 0;
+    int64_t N = 0;        // local samples
+    int64_t nTiles = 0;   // ceil(N / 32)
+    bool ready = false;   // u uploaded
+    int kernelChoice = MBAR_B200_KERNEL_AUTO;
+    int smCount = 148;
+
+    std::vector<double> h_Nk;       // [K]
+    std::vector<double> h_logNk;    // [K], -inf for unsampled
+    std::vector<int> active;        // indices of sampled states
+    int firstActive = 0;
+    double N_total_states = 0;      // sum_k N_k (global N)
+
+    double* d_u = nullptr;          // [nTiles][K][32] shifted, clamped
+    double* d_xshift = nullptr;     // [nTiles*32] per-sample shift x_n = min over sampled k of u_kn
+    double sumX = 0.0;              // sum_n x_n over valid local samples
+    double* d_c = nullptr;          // [2][K] c_k = f_k + log N_k - mid (fused) | f_k (row K..2K)
+    double* d_Nk = nullptr;         // [K]
+    unsigned long long* d_rowmask = nullptr;  // [ceil(K/64)] bit per sampled state
+    double* d_partial = nullptr;    // [MAX_GRID][K+2] per-CTA partials
+    double* d_out = nullptr;        // PassLayout packed result (with G)
+    double* h_out = nullptr;        // pinned mirror of d_out
+    double* d_L = nullptr;          // [nTiles*32] per-sample L_n (lazy)
+    double* d_W = nullptr;          // reserved
+    unsigned int* d_ticket = nullptr;
+    int* d_flag = nullptr;          // [4] error/diagnostic flags
+    double* d_f = nullptr;          // [4][K] device-resident f vectors for native loops
+    double* h_f = nullptr;          // pinned [4][K]
+    double* d_scratch = nullptr;    // misc K*K scratch
+    cudaStream_t stream = nullptr;
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evA = nullptr, evB = nullptr;
+    cudaEvent_t evCopy[2] = {nullptr, nullptr};
+    double* stage_pinned[2] = {nullptr, nullptr};
+    double* stage_dev[2] = {nullptr, nullptr};
+    int64_t stageCols = 0;
+
+    // communicator (NCCL, dlopen'd)
+    void* comm = nullptr;
+    int nranks = 1, rank = 0;
+
+    // counters
+    int64_t launches = 0, passes = 0, h2dBytes = 0, d2hBytes = 0;
+    double lastPassMs = 0.0;
+    bool timePasses = true;
+};
+
+namespace mbar {
+
+struct FusedParams {
+    const double* u;
+    const double* c;                       // [K] f_k + log N_k - mid (sampled rows)
+    const unsigned long long* rowmask;
+    const double* Nk;
+    double* partial;                       // [grid][K + 2]
+    double* out;
+    unsigned int* ticket;
+    double* Lout;                          // [nTiles*32] shifted-frame L'_n, or NULL
+    int64_t N, nTiles, nStages;
+    double mid;
+    int K, Wk, Wn, Rw, TPW, NS;
+    uint32_t tileBytes, stageBytes;
+};
+
+// ---- host-side helpers implemented across the .cu files ----
+int retile_chunk(mbar_b200_ctx* ctx, const double* d_rowmajor, int64_t ldCols, int64_t tile0,
+                 int64_t nTilesChunk, int64_t validCols, cudaStream_t s);
+int launch_pass_generic(mbar_b200_ctx* ctx, const double* h_f, bool wantL);
+int launch_pass_fused(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool* usedOut);
+int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams* out, bool* ok);
+int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p);
+bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, double* midOut);
+int launch_hessian(mbar_b200_ctx* ctx, const double* h_f);
+int launch_logw(mbar_b200_ctx* ctx, const double* h_f, double* logW_host, int64_t ld, int expo);
+int launch_synth(mbar_b200_ctx* ctx, const mbar_b200_synth* spec);
+int launch_untile(mbar_b200_ctx* ctx, int64_t n0, int64_t n, double* d_dst, int64_t ld);
+int comm_allreduce(mbar_b200_ctx* ctx, double* d_buf, int count, int op /*0 sum, 2 max*/);
+int reduce_sumx(mbar_b200_ctx* ctx);
+
+// ---- device helpers ----
+#ifdef __CUDACC__
+static __device__ const double MBAR_EXP_TABLE[MBAR_EXP_NT] = {MBAR_EXP_TABLE_VALUES};
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// 1-D bulk async copy global -> shared (TMA engine; SASS UBLKCP), completion on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+constexpr double EXP_MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+
+// exp(a) with the binary exponent kept apart:  exp(a) = v * 2^q,  v in [1, 2).
+// a in [-5e7, 5e7]; `tab` = 32-entry table of 2^(j/32) in shared memory (conflict-free: 256 B).
+// 9 fp64 pipe ops (FMA t, ADD nf, FMA r, 4 FMA Horner, MUL, FMA) + integer work on the ALU pipe.
+__device__ __forceinline__ void exp_split(double a, const double* __restrict__ tab, double& v, int& q) {
+    const double t = fma(a, MBAR_EXP_SCALE, EXP_MAGIC);
+    const int n = __double2loint(t);
+    const double nf = t - EXP_MAGIC;
+    const double r = fma(nf, -MBAR_EXP_LN2N, a);
+    double p = fma(MBAR_EXP_C5, r, MBAR_EXP_C4);
+    p = fma(p, r, MBAR_EXP_C3);
+    p = fma(p, r, MBAR_EXP_C2);
+    p = fma(p, r, MBAR_EXP_C1);
+    p = p * r;
+    const double T = tab[n & (MBAR_EXP_NT - 1)];
+    v = fma(T, p, T);
+    q = n >> 5;
+}
+// v * 2^q with q clamped to the normal range from below (result >= ~2^-1021, never denormal) and
+// assumed < 1023 from above.
+__device__ __forceinline__ double scale2(double v, int q) {
+    q = max(q, -1021);
+    const int hi = __double2hiint(v) + (q << 20);
+    return __hiloint2double(hi, __double2loint(v));
+}
+__device__ __forceinline__ double exp_fast(double a, const double* __restrict__ tab) {
+    double v;
+    int q;
+    exp_split(a, tab, v, q);
+    return scale2(v, q);
+}
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+#endif
+
+}  // namespace mbar

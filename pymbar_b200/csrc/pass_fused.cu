@@ -1,0 +1,296 @@
+// Fused streaming pass for K <= 256 sampled+unsampled rows: ONE read of u_kn per iteration.
+//
+// Reference being replaced: the two logsumexp sweeps of self_consistent_update / mbar_gradient /
+// mbar_objective (mbar_solvers.py:231-242, :284-292, :327-355).  One launch yields S_k = sum_n W_nk and
+// sum_n L_n, from which  f_sci = f - log S,  g = N (S - 1),  obj = sum L - N.f  all follow.
+//
+// Structure (persistent, one CTA per SM, 8 consumer warps + 1 producer warp):
+//   * producer lane streams whole stages (contiguous extents of the tile-major layout) into a
+//     3..8-deep shared-memory ring with cp.async.bulk (TMA engine) completing on mbarriers;
+//   * consumers: lane = sample, warp = contiguous chunk of <= R states.  Each thread pulls its
+//     R energies out of shared memory ONCE, does one fp64 exp per entry with the binary exponent
+//     handled on the integer pipe, and keeps R per-state accumulators in registers for the whole
+//     kernel — no shuffles, no atomics, no re-reads in the steady state;
+//   * the per-sample denominator is exchanged between the Wk warps that share a sample group through
+//     4 KB of shared memory and one named barrier per tile (none when K <= 32);
+//   * per-CTA partials -> global, last CTA (ticket) reduces them in CTA order: deterministic.
+//
+// No per-sample max is needed: samples are pre-shifted so that min over sampled k of u'_kn = 0, hence
+// max_k (c_k - u'_kn) lies in [min c, max c]; with c centred on `mid` and max c - min c < 1200 every
+// exponent stays inside the fp64 range.  The kernel still verifies D_n per sample and raises a flag
+// (host falls back to the generic kernel) if that assumption is ever violated.
+//
+// fp64 pipe budget per (k, n) entry: 1 (c - u) + 9 (exp) + 1 (D +=) + 1 (acc FMA) = 12 ops.
+#include <cmath>
+
+#include "internal.cuh"
+
+namespace mbar {
+
+
+constexpr int FUSED_CONSUMER_WARPS = 8;
+constexpr int FUSED_THREADS = (FUSED_CONSUMER_WARPS + 1) * 32;
+constexpr uint32_t FUSED_COPY_CHUNK = 32768;
+
+__host__ __device__ inline size_t fused_smem_header(int K) {
+    // tab[32] | c_s[K] | xD[2][8][32] | sred[256] | sumL[8] | bad[8] | full[8] | empty[8]
+    size_t b = 256 + (size_t)K * 8 + 2 * 8 * 32 * 8 + 256 * 8 + 64 + 64 + 64 + 64;
+    return (b + 127) & ~(size_t)127;
+}
+
+template <int R>
+__global__ void __launch_bounds__(FUSED_THREADS, 1) pass_fused_kernel(const FusedParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int K = p.K;
+    double* tab = reinterpret_cast<double*>(smem_raw);
+    double* c_s = tab + 32;
+    double* xD = c_s + K;                        // [2][8 warps][32]
+    double* sred = xD + 2 * 8 * 32;              // [Wn][K]  (Wn * K <= 256)
+    double* s_sumL = sred + 256;                 // [8]
+    int* s_bad = reinterpret_cast<int*>(s_sumL + 8);          // [8] (+pad)
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_sumL + 16);
+    uint64_t* bar_empty = bar_full + 8;
+    unsigned char* stages = smem_raw + fused_smem_header(K);
+    __shared__ bool s_last;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 32) tab[threadIdx.x] = MBAR_EXP_TABLE[threadIdx.x];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) c_s[k] = p.c[k];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.NS; ++i) {
+            mbar_init(smem_u32(&bar_full[i]), 1);
+            mbar_init(smem_u32(&bar_empty[i]), FUSED_CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int tilesPerStage = p.Wn * p.TPW;
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.0;
+    double sumL = 0.0;
+    int bad = 0;
+    const int g = warp / p.Wk, w = warp % p.Wk;   // sample group, state chunk (consumers)
+    const int k0 = w * p.Rw;
+
+    if (warp == FUSED_CONSUMER_WARPS) {
+        // ------------------------------ producer ------------------------------
+        if (lane == 0) {
+            int it = 0;
+            for (int64_t s = blockIdx.x; s < p.nStages; s += gridDim.x, ++it) {
+                const int slot = it % p.NS;
+                if (it >= p.NS) mbar_wait(smem_u32(&bar_empty[slot]), ((it / p.NS) - 1) & 1);
+                const int64_t tile0 = s * tilesPerStage;
+                const int64_t ntl = min((int64_t)tilesPerStage, p.nTiles - tile0);
+                const uint32_t bytes = (uint32_t)ntl * p.tileBytes;
+                const uint32_t fb = smem_u32(&bar_full[slot]);
+                mbar_arrive_expect_tx(fb, bytes);
+                const unsigned char* src =
+                    reinterpret_cast<const unsigned char*>(p.u) + (size_t)tile0 * p.tileBytes;
+                const uint32_t dst = smem_u32(stages + (size_t)slot * p.stageBytes);
+                for (uint32_t off = 0; off < bytes; off += FUSED_COPY_CHUNK)
+                    bulk_g2s(dst + off, src + off, min(FUSED_COPY_CHUNK, bytes - off), fb);
+            }
+        }
+    } else {
+        // ------------------------------ consumers -----------------------------
+        uint32_t actbits = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = k0 + r;
+            if (r < p.Rw && k < K && ((p.rowmask[k >> 6] >> (k & 63)) & 1ull)) actbits |= 1u << r;
+        }
+        int par = 0;
+        int it = 0;
+        for (int64_t s = blockIdx.x; s < p.nStages; s += gridDim.x, ++it) {
+            const int slot = it % p.NS;
+            mbar_wait(smem_u32(&bar_full[slot]), (it / p.NS) & 1);
+            const double* sb = reinterpret_cast<const double*>(stages + (size_t)slot * p.stageBytes);
+            for (int j = 0; j < p.TPW; ++j) {
+                const int tis = j * p.Wn + g;
+                const int64_t tile = s * tilesPerStage + tis;
+                if (tile >= p.nTiles) break;   // uniform over the sample group
+                const double* tp = sb + ((size_t)tis * K + k0) * TILE_N + lane;
+                double e[R];
+                double Dp = 0.0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((actbits >> r) & 1u) {
+                        const double a = c_s[k0 + r] - tp[r * TILE_N];
+                        e[r] = exp_fast(a, tab);
+                        Dp += e[r];
+                    } else {
+                        e[r] = 0.0;
+                    }
+                }
+                double D = Dp;
+                if (p.Wk > 1) {
+                    double* x = xD + (par * 8 + g * p.Wk) * 32 + lane;
+                    x[w * 32] = Dp;
+                    named_bar_sync(1 + g, p.Wk * 32);
+                    D = 0.0;
+                    for (int ww = 0; ww < p.Wk; ++ww) D += x[ww * 32];
+                    par ^= 1;
+                }
+                const bool valid = tile * TILE_N + lane < p.N;
+                if (valid && !(D > 1e-250 && D < 1e250)) bad = 1;
+                const double invD = valid ? 1.0 / D : 0.0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r] = fma(e[r], invD, acc[r]);
+                if (w == 0) {
+                    const double logD = log(D);
+                    if (valid) sumL += logD;
+                    if (p.Lout) p.Lout[tile * TILE_N + lane] = logD + p.mid;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_empty[slot]));
+        }
+        // per-warp lane reduction of the R accumulators (once per kernel)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double t = warp_sum(acc[r]);
+            if (lane == 0 && r < p.Rw && k0 + r < K) sred[g * K + k0 + r] = t;
+        }
+        sumL = warp_sum(sumL);
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            s_sumL[warp] = (w == 0) ? sumL : 0.0;
+            s_bad[warp] = bad;
+        }
+    }
+    __syncthreads();
+
+    double* P = p.partial + (size_t)blockIdx.x * (K + 2);
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        double t = 0.0;
+        for (int gg = 0; gg < p.Wn; ++gg) t += sred[gg * K + k];
+        P[k] = t;
+    }
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        int b = 0;
+        for (int i = 0; i < FUSED_CONSUMER_WARPS; ++i) {
+            t += s_sumL[i];
+            b |= s_bad[i];
+        }
+        P[K] = t;
+        P[K + 1] = (double)b;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicInc(p.ticket, gridDim.x - 1);
+        s_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const PassLayout lay{K};
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const bool act = (p.rowmask[k >> 6] >> (k & 63)) & 1ull;
+        double t = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) t += p.partial[(size_t)b * (K + 2) + k];
+        p.out[lay.S() + k] = act ? t / p.Nk[k] : 0.0;
+        p.out[lay.logS() + k] = 0.0;
+    }
+    if (threadIdx.x == 0) {
+        double t = 0.0, b = 0.0;
+        for (unsigned i = 0; i < gridDim.x; ++i) {
+            t += p.partial[(size_t)i * (K + 2) + K];
+            b += p.partial[(size_t)i * (K + 2) + K + 1];
+        }
+        p.out[lay.sumL()] = t + (double)p.N * p.mid;
+        p.out[lay.flag()] = b;
+    }
+}
+
+bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, double* midOut) {
+    if (ctx->K > 256) return false;
+    double lo = INFINITY, hi = -INFINITY;
+    for (int k : ctx->active) {
+        const double c = h_f[k] + ctx->h_logNk[k];
+        if (!std::isfinite(c)) return false;
+        lo = std::fmin(lo, c);
+        hi = std::fmax(hi, c);
+    }
+    if (hi - lo >= FUSED_SPREAD) return false;
+    if (std::fabs(hi) > C_RANGE || std::fabs(lo) > C_RANGE) return false;
+    if (midOut) *midOut = 0.5 * (hi + lo);
+    return true;
+}
+
+// Configure the fused kernel for f (host) and stage c = f + log N - mid on the device.
+int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams* out, bool* ok) {
+    *ok = false;
+    double mid = 0.0;
+    if (!fused_applicable(ctx, h_f, &mid)) return MBAR_B200_OK;
+    const int K = ctx->K;
+    FusedParams p{};
+    p.K = K;
+    p.Wk = K <= 32 ? 1 : K <= 64 ? 2 : K <= 128 ? 4 : 8;
+    p.Wn = FUSED_CONSUMER_WARPS / p.Wk;
+    p.Rw = (K + p.Wk - 1) / p.Wk;
+    p.tileBytes = (uint32_t)K * TILE_N * 8;
+    int tpw = (int)(65536u / (p.Wn * p.tileBytes));
+    p.TPW = tpw < 1 ? 1 : (tpw > 8 ? 8 : tpw);
+    p.stageBytes = (uint32_t)p.Wn * p.TPW * p.tileBytes;
+    const size_t header = fused_smem_header(K);
+    int ns = (int)((225 * 1024 - header) / p.stageBytes);
+    p.NS = ns > 8 ? 8 : ns;
+    if (p.NS < 2) return MBAR_B200_OK;
+    const int tilesPerStage = p.Wn * p.TPW;
+    p.nStages = (ctx->nTiles + tilesPerStage - 1) / tilesPerStage;
+    p.N = ctx->N;
+    p.nTiles = ctx->nTiles;
+    p.mid = mid;
+    p.u = ctx->d_u;
+    p.c = ctx->d_c;
+    p.rowmask = ctx->d_rowmask;
+    p.Nk = ctx->d_Nk;
+    p.partial = ctx->d_partial;
+    p.out = ctx->d_out;
+    p.ticket = ctx->d_ticket;
+    if (wantL && !ctx->d_L)
+        MBAR_CUDA(cudaMalloc((void**)&ctx->d_L, (size_t)ctx->nTiles * TILE_N * sizeof(double)));
+    p.Lout = wantL ? ctx->d_L : nullptr;
+    for (int k = 0; k < K; ++k)
+        ctx->h_f[k] = std::isinf(ctx->h_logNk[k]) ? 0.0 : h_f[k] + ctx->h_logNk[k] - mid;
+    MBAR_CUDA(cudaMemcpyAsync(ctx->d_c, ctx->h_f, (size_t)K * sizeof(double), cudaMemcpyHostToDevice,
+                              ctx->stream));
+    ctx->h2dBytes += K * 8;
+    *out = p;
+    *ok = true;
+    return MBAR_B200_OK;
+}
+
+// Launch with whatever c currently sits in ctx->d_c (device-resident iteration).
+int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
+    const size_t smem = fused_smem_header(p.K) + (size_t)p.NS * p.stageBytes;
+    int64_t grid = p.nStages < ctx->smCount ? p.nStages : ctx->smCount;
+    void (*kern)(const FusedParams) =
+        p.Rw <= 8 ? pass_fused_kernel<8> : p.Rw <= 16 ? pass_fused_kernel<16> : pass_fused_kernel<32>;
+    static bool attrSet[3] = {false, false, false};
+    const int which = p.Rw <= 8 ? 0 : p.Rw <= 16 ? 1 : 2;
+    if (!attrSet[which]) {
+        MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attrSet[which] = true;
+    }
+    MBAR_CUDA(cudaEventRecord(ctx->evA, ctx->stream));
+    kern<<<(unsigned)grid, FUSED_THREADS, smem, ctx->stream>>>(p);
+    MBAR_CUDA(cudaEventRecord(ctx->evB, ctx->stream));
+    ctx->launches++;
+    ctx->passes++;
+    MBAR_CUDA(cudaGetLastError());
+    return MBAR_B200_OK;
+}
+
+int launch_pass_fused(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool* usedOut) {
+    FusedParams p;
+    MBAR_TRY(fused_prepare(ctx, h_f, wantL, &p, usedOut));
+    if (!*usedOut) return MBAR_B200_OK;
+    return fused_enqueue(ctx, p);
+}
+
+}  // namespace mbar

@@ -1,0 +1,228 @@
+"""DeviceProblem: one (u_kn, N_k) data set resident in HBM on one GPU (one shard of the samples).
+
+Thin object wrapper over the C ABI (include/mbar_b200.h).  All math happens in libmbar_b200.so;
+this file only marshals numpy buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import SolveResult, check
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _f64(a, K=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if K is not None and a.shape != (K,):
+        raise ValueError(f"expected shape ({K},), got {a.shape}")
+    return a
+
+
+class PinnedArray:
+    """float64 ndarray backed by cudaHostAlloc memory (mbar_b200_host_alloc)."""
+
+    def __init__(self, shape):
+        self.shape = tuple(int(s) for s in shape)
+        n = int(np.prod(self.shape))
+        self._ptr = C.c_void_p()
+        check(_lib.load().mbar_b200_host_alloc(C.byref(self._ptr), n * 8))
+        buf = (C.c_double * n).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=np.float64).reshape(self.shape)
+
+    def free(self):
+        if self._ptr is not None and self._ptr.value:
+            self.array = None
+            _lib.load().mbar_b200_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceProblem:
+    """u_kn [K, N_local] + global N_k [K] on one B200.
+
+    Parameters
+    ----------
+    u_kn : ndarray [K, N_local] float64 (any strides with unit inner stride), or None to allocate
+        only (fill later with :meth:`synthesize` / :meth:`upload`).
+    N_k : array [K] — GLOBAL sample counts (all ranks), int or float; zeros mark unsampled states.
+    device : CUDA device ordinal.
+    N_local : required when u_kn is None.
+    """
+
+    def __init__(self, u_kn, N_k, device=0, N_local=None):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        N_k = _f64(N_k)
+        if N_k.ndim != 1:
+            raise ValueError("N_k must be 1-D")
+        self.K = int(N_k.shape[0])
+        self.N_k = N_k
+        if u_kn is not None:
+            if u_kn.ndim != 2 or u_kn.shape[0] != self.K:
+                raise ValueError(f"u_kn must be [K={self.K}, N], got {u_kn.shape}")
+            N_local = u_kn.shape[1]
+        if N_local is None:
+            raise ValueError("N_local is required when u_kn is None")
+        self.N = int(N_local)
+        self.device = int(device)
+        check(self._lib.mbar_b200_create(C.byref(self._h), self.device, self.K, self.N, _dptr(N_k)))
+        if u_kn is not None:
+            self.upload(u_kn)
+
+    # ---- lifetime -------------------------------------------------------------------------
+    def close(self):
+        if self._h is not None and self._h.value:
+            self._lib.mbar_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- data -------------------------------------------------------------------------------
+    def upload(self, u_kn):
+        u = np.asarray(u_kn)
+        if u.dtype != np.float64 or u.ndim != 2 or u.strides[1] != 8 or u.strides[0] % 8 or u.strides[0] < 8 * u.shape[1]:
+            u = np.ascontiguousarray(u, dtype=np.float64)
+        if u.shape != (self.K, self.N):
+            raise ValueError(f"u_kn must be [{self.K}, {self.N}], got {u.shape}")
+        check(self._lib.mbar_b200_upload_u_kn(self._h, C.c_void_p(u.ctypes.data), u.strides[0] // 8))
+
+    def upload_device_ptr(self, ptr, ld):
+        check(self._lib.mbar_b200_upload_u_kn_dev(self._h, C.c_void_p(int(ptr)), int(ld)))
+
+    def synthesize(self, O_k, k_k, seed=0, n_offset=0, N_global=None):
+        O_k, k_k = _f64(O_k, self.K), _f64(k_k, self.K)
+        spec = _lib.Synth(int(seed), int(n_offset), int(N_global if N_global is not None else self.N),
+                          _dptr(O_k), _dptr(k_k))
+        check(self._lib.mbar_b200_synthesize(self._h, C.byref(spec)))
+
+    def download(self, n0=0, n=None, out=None):
+        n = self.N - n0 if n is None else n
+        if out is None:
+            out = np.empty((self.K, n), np.float64)
+        check(self._lib.mbar_b200_download_u_kn(self._h, int(n0), int(n), C.c_void_p(out.ctypes.data),
+                                                out.strides[0] // 8))
+        return out
+
+    def set_kernel(self, which):
+        code = {"auto": 0, "fused": 1, "generic": 2}.get(which, which)
+        check(self._lib.mbar_b200_set_pass_kernel(self._h, int(code)))
+
+    def counters(self):
+        v = [C.c_int64(0) for _ in range(4)]
+        check(self._lib.mbar_b200_get_counters(self._h, *[C.byref(x) for x in v]))
+        return dict(launches=v[0].value, passes=v[1].value, h2d_bytes=v[2].value, d2h_bytes=v[3].value)
+
+    def last_pass_ms(self):
+        ms = C.c_double(0)
+        check(self._lib.mbar_b200_last_pass_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    # ---- communicator -------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        buf = C.create_string_buffer(_lib.UNIQUE_ID_BYTES)
+        check(_lib.load().mbar_b200_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, nranks, rank, unique_id):
+        buf = C.create_string_buffer(bytes(unique_id), _lib.UNIQUE_ID_BYTES)
+        check(self._lib.mbar_b200_comm_init(self._h, int(nranks), int(rank), buf))
+
+    # ---- the pass and the reference primitives ----------------------------------------------------
+    def streaming_pass(self, f_k, want_G=False):
+        f = _f64(f_k, self.K)
+        S = np.empty(self.K)
+        sumL = C.c_double(0)
+        G = np.empty((self.K, self.K)) if want_G else None
+        check(self._lib.mbar_b200_pass(self._h, _dptr(f), _dptr(S), C.byref(sumL),
+                                       _dptr(G) if want_G else None))
+        return S, sumL.value, G
+
+    def self_consistent_update(self, f_k):
+        f = _f64(f_k, self.K)
+        out = np.empty(self.K)
+        check(self._lib.mbar_b200_self_consistent_update(self._h, _dptr(f), _dptr(out)))
+        return out
+
+    def gradient(self, f_k):
+        f = _f64(f_k, self.K)
+        out = np.empty(self.K)
+        check(self._lib.mbar_b200_gradient(self._h, _dptr(f), _dptr(out)))
+        return out
+
+    def objective_and_gradient(self, f_k):
+        f = _f64(f_k, self.K)
+        g = np.empty(self.K)
+        obj = C.c_double(0)
+        check(self._lib.mbar_b200_objective_and_gradient(self._h, _dptr(f), C.byref(obj), _dptr(g)))
+        return obj.value, g
+
+    def objective(self, f_k):
+        f = _f64(f_k, self.K)
+        obj = C.c_double(0)
+        check(self._lib.mbar_b200_objective_and_gradient(self._h, _dptr(f), C.byref(obj), None))
+        return obj.value
+
+    def hessian(self, f_k):
+        f = _f64(f_k, self.K)
+        H = np.empty((self.K, self.K))
+        check(self._lib.mbar_b200_hessian(self._h, _dptr(f), _dptr(H)))
+        return H
+
+    def log_W_nk(self, f_k, exponentiate=False, out=None):
+        f = _f64(f_k, self.K)
+        if out is None:
+            out = np.empty((self.N, self.K), np.float64)
+        check(self._lib.mbar_b200_log_W_nk(self._h, _dptr(f), C.c_void_p(out.ctypes.data),
+                                           out.strides[0] // 8, int(bool(exponentiate))))
+        return out
+
+    def log_denominator(self, f_k):
+        f = _f64(f_k, self.K)
+        out = np.empty(self.N)
+        check(self._lib.mbar_b200_log_denominator(self._h, _dptr(f), _dptr(out)))
+        return out
+
+    # ---- native loops ---------------------------------------------------------------------------
+    @staticmethod
+    def _result(r):
+        return {name: getattr(r, name) for name, _ in SolveResult._fields_}
+
+    def solve_sci(self, f_k, tol=1e-12, maxiter=10000):
+        f = _f64(f_k, self.K).copy()
+        r = SolveResult()
+        check(self._lib.mbar_b200_solve_sci(self._h, _dptr(f), float(tol), int(maxiter), C.byref(r)))
+        return f, self._result(r)
+
+    def solve_adaptive(self, f_k, tol=1e-12, maxiter=10000, min_sc_iter=2, gamma=1.0):
+        f = _f64(f_k, self.K).copy()
+        r = SolveResult()
+        check(self._lib.mbar_b200_solve_adaptive(self._h, _dptr(f), float(tol), int(maxiter), int(min_sc_iter),
+                                                 float(gamma), C.byref(r)))
+        return f, self._result(r)
+
+    def sci_iterate(self, f_k, iters):
+        f = _f64(f_k, self.K).copy()
+        check(self._lib.mbar_b200_sci_iterate(self._h, _dptr(f), int(iters)))
+        return f

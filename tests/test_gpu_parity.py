@@ -1,0 +1,166 @@
+"""GPU parity: the CUDA path (through the C ABI) vs the CPU oracle and the reference-generated
+fixtures, on the same inputs.  Tolerances: |delta f| < 1e-8 (BASELINE.json north_star); primitives
+are held much tighter (1e-10 .. 1e-12) because only reduction order and exp rounding differ."""
+import numpy as np
+import pytest
+
+from oracle import mbar_oracle as orc
+from tests import _cases
+
+pytestmark = pytest.mark.gpu
+
+TOL_F = 1e-8
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import pymbar_b200
+    from pymbar_b200 import _lib
+
+    _lib.load()
+    if _lib.device_count() == 0:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box")
+    return pymbar_b200
+
+
+@pytest.mark.parametrize("kernel", ["fused", "generic"])
+@pytest.mark.parametrize("name", _cases.ALL)
+def test_primitives(lib, name, kernel):
+    z = _cases.load(name)
+    u, N = z["u_kn"], z["N_k"].astype(float)
+    s = N > 0
+    K = len(N)
+    with lib.DeviceProblem(u, N) as p:
+        p.set_kernel(kernel if (kernel == "generic" or K <= 256) else "auto")
+        for tag, f in (("zero", np.zeros(K)), ("rand", z["f_rand"])):
+            # self-consistent update: all states, fixture produced by the real reference
+            np.testing.assert_allclose(p.self_consistent_update(f), z[f"{tag}_sci"], rtol=0, atol=1e-10)
+            g = p.gradient(f)
+            np.testing.assert_allclose(g[s], z[f"{tag}_grad"], rtol=1e-10, atol=1e-9 * N.max())
+            assert np.all(g[~s] == 0)
+            # objective: reference value is for the sampled sub-problem; unsampled rows have N_k f_k = 0
+            np.testing.assert_allclose(p.objective(f), z[f"{tag}_obj"], rtol=1e-12, atol=1e-7)
+            H = p.hessian(f)[np.ix_(s, s)]
+            if f"{tag}_hess" in z:
+                np.testing.assert_allclose(H, z[f"{tag}_hess"], rtol=1e-10, atol=1e-10)
+                np.testing.assert_allclose(p.log_W_nk(f), z[f"{tag}_logW"], rtol=0, atol=1e-10)
+            else:
+                np.testing.assert_allclose(np.diag(H), z[f"{tag}_hess_diag"], rtol=1e-10)
+                np.testing.assert_allclose(np.linalg.norm(H), z[f"{tag}_hess_fro"], rtol=1e-10)
+                np.testing.assert_allclose(p.log_W_nk(f)[:4], z[f"{tag}_logW_head"], atol=1e-10)
+
+
+@pytest.mark.parametrize("name", _cases.SMALL + ["osc_50x100"])
+def test_pass_outputs_vs_oracle(lib, name):
+    z = _cases.load(name)
+    u, N = z["u_kn"], z["N_k"].astype(float)
+    s = N > 0
+    f = z["f_rand"]
+    with lib.DeviceProblem(u, N) as p:
+        S, sumL, G = p.streaming_pass(f, want_G=True)
+        S_ref, L_ref = orc.single_pass_sums(u[s], N[s], f[s])
+        np.testing.assert_allclose(S[s], S_ref, rtol=1e-11)
+        np.testing.assert_allclose(sumL, L_ref.sum(), rtol=1e-12)
+        W = orc.mbar_W_nk(u[s], N[s], f[s])
+        np.testing.assert_allclose(G[np.ix_(s, s)], W.T @ W, rtol=1e-10, atol=1e-14)
+        np.testing.assert_allclose(p.log_denominator(f), orc.log_denominator_n(u[s], N[s], f[s]), atol=1e-11)
+        W_dev = p.log_W_nk(f, exponentiate=True)
+        np.testing.assert_allclose(W_dev[:, s], W, rtol=1e-10, atol=1e-300)
+
+
+@pytest.mark.parametrize("proto", ["default", "robust", "adaptive"])
+@pytest.mark.parametrize("name", _cases.ALL)
+def test_solved_f_k(lib, name, proto):
+    """solve_mbar_for_all_states through the mirrored module API == reference MBAR.f_k."""
+    z = _cases.load(name)
+    ms = lib.mbar_solvers
+    protocol = {"default": ms.DEFAULT_SOLVER_PROTOCOL, "robust": ms.ROBUST_SOLVER_PROTOCOL,
+                "adaptive": ms.BOOTSTRAP_SOLVER_PROTOCOL}[proto]
+    protocol = tuple({k: (dict(v) if isinstance(v, dict) else v) for k, v in st.items()} for st in protocol)
+    N_k = z["N_k"]
+    sws = np.where(N_k != 0)[0]
+    f = ms.solve_mbar_for_all_states(z["u_kn"], N_k, np.zeros(len(N_k)), sws, protocol)
+    assert np.max(np.abs(f - z[f"fk_{proto}"])) < TOL_F
+    # the four invariants of pymbar/tests/test_mbar_solvers.py:34-41, evaluated by the ORACLE
+    Nf = N_k.astype(float)
+    s = Nf > 0
+    np.testing.assert_allclose(orc.mbar_gradient(z["u_kn"][s], Nf[s], f[s]), 0, atol=1e-8 * max(1, Nf.max() / 100))
+    np.testing.assert_allclose(orc.self_consistent_update(z["u_kn"], Nf, f) - f, 0, atol=1e-10)
+    W = orc.mbar_W_nk(z["u_kn"], Nf, f)
+    np.testing.assert_allclose(W.sum(0), 1, atol=1e-9)
+    np.testing.assert_allclose(W @ Nf, 1, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["small_osc_8x40", "small_empty_state", "osc_50x100"])
+def test_native_loops(lib, name):
+    z = _cases.load(name)
+    u, N = z["u_kn"], z["N_k"].astype(float)
+    s = N > 0
+    K = len(N)
+    with lib.DeviceProblem(u, N) as p:
+        f_ad, r = p.solve_adaptive(np.zeros(K), tol=1e-12, min_sc_iter=0)
+        assert r["success"]
+        ref = np.zeros(K)
+        ref[s] = z["adaptive_x"]
+        assert np.max(np.abs(f_ad[s] - ref[s])) < TOL_F
+        f_sci, r2 = p.solve_sci(np.zeros(K), tol=1e-13, maxiter=20000)
+        assert r2["success"] and np.max(np.abs(f_sci[s] - ref[s])) < 1e-7
+        # device-resident iteration == host-stepped self-consistent iteration
+        f0 = np.zeros(K)
+        f_dev = p.sci_iterate(f0, 5)
+        f_host = f0.copy()
+        for _ in range(5):
+            nxt = orc.self_consistent_update(u[s], N[s], f_host[s])
+            f_host[s] = nxt - nxt[0]
+        np.testing.assert_allclose(f_dev[s], f_host[s], atol=1e-11)
+
+
+def test_upload_layouts_and_roundtrip(lib):
+    z = _cases.load("small_osc_8x40")
+    u, N = z["u_kn"], z["N_k"].astype(float)
+    f = z["f_rand"]
+    with lib.DeviceProblem(u, N) as p:
+        want = p.self_consistent_update(f)
+        back = p.download()
+        np.testing.assert_allclose(back, u, rtol=0, atol=1e-12 * np.abs(u).max())
+    big = np.zeros((u.shape[0], u.shape[1] + 7))
+    big[:, 3:3 + u.shape[1]] = u
+    view = big[:, 3:3 + u.shape[1]]                      # non-contiguous rows (ld > N)
+    pin = lib.PinnedArray(u.shape)
+    pin.array[:] = u
+    for src in (view, pin.array, np.asfortranarray(u), u.astype(np.float32).astype(np.float64)):
+        with lib.DeviceProblem(src, N) as p:
+            np.testing.assert_allclose(p.self_consistent_update(f), want, atol=1e-12)
+    pin.free()
+
+
+def test_errors(lib):
+    from pymbar_b200._lib import MbarB200Error
+
+    z = _cases.load("small_exp_6x50")
+    u, N = z["u_kn"].copy(), z["N_k"].astype(float)
+    u[2, 5] = np.nan
+    with pytest.raises(MbarB200Error) as e:
+        lib.DeviceProblem(u, N)
+    assert e.value.status == -5
+    u[2, 5] = np.inf                                      # +inf energy is legal: weight 0
+    with lib.DeviceProblem(u, N) as p:
+        f = np.zeros(len(N))
+        ref = orc.self_consistent_update(u, N, f)
+        np.testing.assert_allclose(p.self_consistent_update(f), ref, atol=1e-10)
+        with pytest.raises(MbarB200Error) as e2:
+            p.gradient(np.full(len(N), 1e9))
+        assert e2.value.status == -6
+    with pytest.raises(lib.ParameterError):
+        lib.mbar_solvers.solve_mbar_once(z["u_kn"], N, np.zeros(len(N)), method="no-such-method")
+    with pytest.raises(TypeError):
+        lib.mbar_solvers.validate_inputs(z["u_kn"], list(N), np.zeros(len(N)))
+
+
+def test_wide_f_spread_falls_back(lib):
+    """A spread of f_k + log N_k beyond the fused kernel's range must still give oracle results."""
+    z = _cases.load("small_osc_8x40")
+    u, N = z["u_kn"], z["N_k"].astype(float)
+    f = np.linspace(0, 3000, len(N))
+    with lib.DeviceProblem(u, N) as p:
+        np.testing.assert_allclose(p.self_consistent_update(f), orc.self_consistent_update(u, N, f), atol=1e-9)
