@@ -117,7 +117,7 @@ struct FusedParams {
     double* Lout;                          // [nTiles*32] shifted-frame L'_n, or NULL
     int64_t N, nTiles, nStages;
     double mid;
-    int K, Wk, Wn, Rw, TPW, NS;
+    int K, Wk, Wn, Rw, TPW, NS, CW, batch, debugSkip;
     uint32_t tileBytes, stageBytes;
 };
 
@@ -166,6 +166,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
     } while (!done);
+}
+// Same wait for the single producer lane: back off between polls so the spin does not steal issue
+// slots from the consumer warps that share its scheduler.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(0x989680u)
+            : "memory");
+        if (done) break;
+        __nanosleep(200);
+    }
 }
 // 1-D bulk async copy global -> shared (TMA engine; SASS UBLKCP), completion on an mbarrier.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {

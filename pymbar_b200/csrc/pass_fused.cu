@@ -22,33 +22,90 @@
 //
 // fp64 pipe budget per (k, n) entry: 1 (c - u) + 9 (exp) + 1 (D +=) + 1 (acc FMA) = 12 ops.
 #include <cmath>
+#include <cstdlib>
 
 #include "internal.cuh"
 
 namespace mbar {
 
 
-constexpr int FUSED_CONSUMER_WARPS = 8;
-constexpr int FUSED_THREADS = (FUSED_CONSUMER_WARPS + 1) * 32;
+constexpr int FUSED_MAX_CW = 16;   // consumer warps: 8 (R <= 32 rows/thread) or 16 (R <= 16)
 constexpr uint32_t FUSED_COPY_CHUNK = 32768;
 
 __host__ __device__ inline size_t fused_smem_header(int K) {
-    // tab[32] | c_s[K] | xD[2][8][32] | sred[256] | sumL[8] | bad[8] | full[8] | empty[8]
-    size_t b = 256 + (size_t)K * 8 + 2 * 8 * 32 * 8 + 256 * 8 + 64 + 64 + 64 + 64;
+    // tab[32] | c_s[K] | xD[2][16][32] | sred[256] | sumL[16] | bad[16] | full[8] | empty[8]
+    size_t b = 256 + (size_t)K * 8 + 2 * FUSED_MAX_CW * 32 * 8 + 256 * 8 + 128 + 128 + 64 + 64;
     return (b + 127) & ~(size_t)127;
 }
 
-template <int R>
-__global__ void __launch_bounds__(FUSED_THREADS, 1) pass_fused_kernel(const FusedParams p) {
+__device__ __forceinline__ double lds_f64(const double* p) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(smem_u32(p)));
+    return v;
+}
+
+// exp of `B` independent arguments a[i] = c[i] - u[i], stage by stage, so the fp64 pipe always has
+// B independent chains in flight.  Shared-memory latency is hidden explicitly: the table lookups
+// are issued right after the rounding step (5 polynomial stages ahead of their use) and the
+// energies of the NEXT batch are fetched before this batch's polynomial (volatile loads keep their
+// program position; two consumer warps per scheduler cannot hide ~30-cycle LDS otherwise).
+template <int B, bool PREFETCH>
+__device__ __forceinline__ void exp_batch(const double (&cu)[B], const double (&uu)[B],
+                                          int tabHi, int tabLo, double (&e)[B],
+                                          const double* nextC, const double* nextU,
+                                          double (&cn)[B], double (&un)[B]) {
+    double t[B], r[B], pl[B], T[B];
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+        r[i] = cu[i] - uu[i];
+        t[i] = fma(r[i], MBAR_EXP_SCALE, EXP_MAGIC);
+    }
+    // table lookup 2^(j/32), j = n & 31: every lane keeps entry `lane` in two 32-bit registers and
+    // the gather is a pair of index shuffles (the source lane is taken modulo 32 by the hardware):
+    // no address arithmetic, no shared-memory bank conflicts.
+#pragma unroll
+    for (int i = 0; i < B; ++i) {
+        const int n = __double2loint(t[i]);
+        T[i] = __hiloint2double(__shfl_sync(0xffffffffu, tabHi, n), __shfl_sync(0xffffffffu, tabLo, n));
+    }
+    if (PREFETCH) {
+#pragma unroll
+        for (int i = 0; i < B; ++i) un[i] = lds_f64(nextU + i * TILE_N);
+#pragma unroll
+        for (int i = 0; i < B; i += 2) {
+            double2 c2;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c2.x), "=d"(c2.y) : "r"(smem_u32(nextC + i)));
+            cn[i] = c2.x;
+            cn[i + 1] = c2.y;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < B; ++i) r[i] = fma(t[i] - EXP_MAGIC, -MBAR_EXP_LN2N, r[i]);
+#pragma unroll
+    for (int i = 0; i < B; ++i) pl[i] = fma(MBAR_EXP_C5, r[i], MBAR_EXP_C4);
+#pragma unroll
+    for (int i = 0; i < B; ++i) pl[i] = fma(pl[i], r[i], MBAR_EXP_C3);
+#pragma unroll
+    for (int i = 0; i < B; ++i) pl[i] = fma(pl[i], r[i], MBAR_EXP_C2);
+#pragma unroll
+    for (int i = 0; i < B; ++i) pl[i] = fma(pl[i], r[i], MBAR_EXP_C1);
+#pragma unroll
+    for (int i = 0; i < B; ++i) pl[i] = pl[i] * r[i];
+#pragma unroll
+    for (int i = 0; i < B; ++i) e[i] = scale2(fma(T[i], pl[i], T[i]), __double2loint(t[i]) >> 5);
+}
+
+template <int R, bool FULL, int CW, int BATCH>
+__global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int K = p.K;
     double* tab = reinterpret_cast<double*>(smem_raw);
     double* c_s = tab + 32;
-    double* xD = c_s + K;                        // [2][8 warps][32]
-    double* sred = xD + 2 * 8 * 32;              // [Wn][K]  (Wn * K <= 256)
-    double* s_sumL = sred + 256;                 // [8]
-    int* s_bad = reinterpret_cast<int*>(s_sumL + 8);          // [8] (+pad)
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_sumL + 16);
+    double* xD = c_s + K;                        // [2][CW warps][32]
+    double* sred = xD + 2 * FUSED_MAX_CW * 32;   // [Wn][K]  (Wn * K <= 256)
+    double* s_sumL = sred + 256;                 // [16]
+    int* s_bad = reinterpret_cast<int*>(s_sumL + 16);         // [16] (+pad)
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_sumL + 32);
     uint64_t* bar_empty = bar_full + 8;
     unsigned char* stages = smem_raw + fused_smem_header(K);
     __shared__ bool s_last;
@@ -59,7 +116,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pass_fused_kernel(const Fuse
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.NS; ++i) {
             mbar_init(smem_u32(&bar_full[i]), 1);
-            mbar_init(smem_u32(&bar_empty[i]), FUSED_CONSUMER_WARPS);
+            mbar_init(smem_u32(&bar_empty[i]), CW);
         }
         mbar_fence_init();
     }
@@ -74,26 +131,27 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pass_fused_kernel(const Fuse
     const int g = warp / p.Wk, w = warp % p.Wk;   // sample group, state chunk (consumers)
     const int k0 = w * p.Rw;
 
-    if (warp == FUSED_CONSUMER_WARPS) {
-        // ------------------------------ producer ------------------------------
-        if (lane == 0) {
-            int it = 0;
-            for (int64_t s = blockIdx.x; s < p.nStages; s += gridDim.x, ++it) {
-                const int slot = it % p.NS;
-                if (it >= p.NS) mbar_wait(smem_u32(&bar_empty[slot]), ((it / p.NS) - 1) & 1);
-                const int64_t tile0 = s * tilesPerStage;
-                const int64_t ntl = min((int64_t)tilesPerStage, p.nTiles - tile0);
-                const uint32_t bytes = (uint32_t)ntl * p.tileBytes;
-                const uint32_t fb = smem_u32(&bar_full[slot]);
-                mbar_arrive_expect_tx(fb, bytes);
-                const unsigned char* src =
-                    reinterpret_cast<const unsigned char*>(p.u) + (size_t)tile0 * p.tileBytes;
-                const uint32_t dst = smem_u32(stages + (size_t)slot * p.stageBytes);
-                for (uint32_t off = 0; off < bytes; off += FUSED_COPY_CHUNK)
-                    bulk_g2s(dst + off, src + off, min(FUSED_COPY_CHUNK, bytes - off), fb);
-            }
-        }
-    } else {
+    // Producer duty rides on thread 0 (a dedicated producer warp would put a third warp on one
+    // scheduler and cut the register budget of EVERY thread from 255 to 168).  `issue(it)` streams the
+    // it-th stage of this CTA into ring slot it % NS.
+    auto issue = [&](int it2) {
+        const int64_t s2 = (int64_t)blockIdx.x + (int64_t)it2 * gridDim.x;
+        if (s2 >= p.nStages) return;
+        const int slot2 = it2 % p.NS;
+        if (it2 >= p.NS) mbar_wait(smem_u32(&bar_empty[slot2]), ((it2 / p.NS) - 1) & 1);
+        const int64_t tile0 = s2 * tilesPerStage;
+        const int64_t ntl = min((int64_t)tilesPerStage, p.nTiles - tile0);
+        const uint32_t bytes = (uint32_t)ntl * p.tileBytes;
+        const uint32_t fb = smem_u32(&bar_full[slot2]);
+        mbar_arrive_expect_tx(fb, bytes);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.u) + (size_t)tile0 * p.tileBytes;
+        const uint32_t dst = smem_u32(stages + (size_t)slot2 * p.stageBytes);
+        for (uint32_t off = 0; off < bytes; off += FUSED_COPY_CHUNK)
+            bulk_g2s(dst + off, src + off, min(FUSED_COPY_CHUNK, bytes - off), fb);
+    };
+    if (threadIdx.x == 0)
+        for (int i = 0; i < p.NS - 1; ++i) issue(i);
+    {
         // ------------------------------ consumers -----------------------------
         uint32_t actbits = 0;
 #pragma unroll
@@ -103,30 +161,65 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pass_fused_kernel(const Fuse
         }
         int par = 0;
         int it = 0;
+        const int tabHi = __double2hiint(MBAR_EXP_TABLE[lane]);
+        const int tabLo = __double2loint(MBAR_EXP_TABLE[lane]);
         for (int64_t s = blockIdx.x; s < p.nStages; s += gridDim.x, ++it) {
             const int slot = it % p.NS;
+            // keep NS-1 stages in flight: stage it+NS-1 goes into the slot consumed at iteration it-1,
+            // which every warp released before it could pass that iteration's denominator barrier
+            if (threadIdx.x == 0) issue(it + p.NS - 1);
             mbar_wait(smem_u32(&bar_full[slot]), (it / p.NS) & 1);
             const double* sb = reinterpret_cast<const double*>(stages + (size_t)slot * p.stageBytes);
             for (int j = 0; j < p.TPW; ++j) {
+                if (p.debugSkip) break;   // development probe: memory pipeline only
                 const int tis = j * p.Wn + g;
                 const int64_t tile = s * tilesPerStage + tis;
                 if (tile >= p.nTiles) break;   // uniform over the sample group
                 const double* tp = sb + ((size_t)tis * K + k0) * TILE_N + lane;
                 double e[R];
                 double Dp = 0.0;
+                if (FULL) {
+                    // every warp owns exactly R sampled rows: branch-free, 8 rows at a time
+                    constexpr int B = R < BATCH ? R : BATCH;
+                    double cu[B], uu[B];
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if ((actbits >> r) & 1u) {
-                        const double a = c_s[k0 + r] - tp[r * TILE_N];
-                        e[r] = exp_fast(a, tab);
-                        Dp += e[r];
-                    } else {
-                        e[r] = 0.0;
+                    for (int i = 0; i < B; ++i) {
+                        uu[i] = lds_f64(tp + i * TILE_N);
+                        cu[i] = lds_f64(c_s + k0 + i);
+                    }
+
+#pragma unroll
+                    for (int r0 = 0; r0 < R; r0 += B) {
+                        double eb[B], cn[B], un[B];
+                        if (r0 + B < R)
+                            exp_batch<B, true>(cu, uu, tabHi, tabLo, eb, c_s + k0 + r0 + B, tp + (r0 + B) * TILE_N, cn, un);
+                        else
+                            exp_batch<B, false>(cu, uu, tabHi, tabLo, eb, nullptr, nullptr, cn, un);
+#pragma unroll
+                        for (int i = 0; i < B; ++i) {
+                            e[r0 + i] = eb[i];
+                            Dp += eb[i];
+                            if (r0 + B < R) {
+                                cu[i] = cn[i];
+                                uu[i] = un[i];
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if ((actbits >> r) & 1u) {
+                            const double a = c_s[k0 + r] - tp[r * TILE_N];
+                            e[r] = exp_fast(a, tab);
+                            Dp += e[r];
+                        } else {
+                            e[r] = 0.0;
+                        }
                     }
                 }
                 double D = Dp;
                 if (p.Wk > 1) {
-                    double* x = xD + (par * 8 + g * p.Wk) * 32 + lane;
+                    double* x = xD + (par * CW + g * p.Wk) * 32 + lane;
                     x[w * 32] = Dp;
                     named_bar_sync(1 + g, p.Wk * 32);
                     D = 0.0;
@@ -171,7 +264,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pass_fused_kernel(const Fuse
     if (threadIdx.x == 0) {
         double t = 0.0;
         int b = 0;
-        for (int i = 0; i < FUSED_CONSUMER_WARPS; ++i) {
+        for (int i = 0; i < CW; ++i) {
             t += s_sumL[i];
             b |= s_bad[i];
         }
@@ -227,10 +320,22 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams
     double mid = 0.0;
     if (!fused_applicable(ctx, h_f, &mid)) return MBAR_B200_OK;
     const int K = ctx->K;
+    if (K > 256) return MBAR_B200_OK;
     FusedParams p{};
     p.K = K;
-    p.Wk = K <= 32 ? 1 : K <= 64 ? 2 : K <= 128 ? 4 : 8;
-    p.Wn = FUSED_CONSUMER_WARPS / p.Wk;
+    // variant: consumer warps CW and rows per thread.  MBAR_B200_FUSED_VARIANT = "cw,batch" overrides.
+    int cw = 8, batch = 8;
+    if (const char* v = std::getenv("MBAR_B200_FUSED_VARIANT")) std::sscanf(v, "%d,%d", &cw, &batch);
+    if (cw != 16) cw = 8;
+    if (batch != 4 && batch != 16) batch = 8;
+    const int rmax = (cw == 16) ? 16 : 32;
+    int wk = 1;
+    while (wk * rmax < K) wk *= 2;
+    p.Wk = wk;
+    p.CW = cw;
+    p.debugSkip = std::getenv("MBAR_B200_FUSED_SKIP") ? 1 : 0;
+    p.batch = batch;
+    p.Wn = cw / p.Wk;
     p.Rw = (K + p.Wk - 1) / p.Wk;
     p.tileBytes = (uint32_t)K * TILE_N * 8;
     int tpw = (int)(65536u / (p.Wn * p.tileBytes));
@@ -269,16 +374,41 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams
 int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
     const size_t smem = fused_smem_header(p.K) + (size_t)p.NS * p.stageBytes;
     int64_t grid = p.nStages < ctx->smCount ? p.nStages : ctx->smCount;
-    void (*kern)(const FusedParams) =
-        p.Rw <= 8 ? pass_fused_kernel<8> : p.Rw <= 16 ? pass_fused_kernel<16> : pass_fused_kernel<32>;
-    static bool attrSet[3] = {false, false, false};
-    const int which = p.Rw <= 8 ? 0 : p.Rw <= 16 ? 1 : 2;
-    if (!attrSet[which]) {
-        MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attrSet[which] = true;
+    const int Rt = p.Rw <= 8 ? 8 : p.Rw <= 16 ? 16 : 32;
+    const bool full = (p.Rw == Rt) && (p.K == p.Wk * p.Rw) && ((int)ctx->active.size() == p.K);
+    void (*kern)(const FusedParams) = nullptr;
+    int which = 0;
+#define PICK(R_, F_, CW_, B_, ID_)                                                    \
+    if (Rt == R_ && full == F_ && p.CW == CW_ && p.batch == B_) {                     \
+        kern = pass_fused_kernel<R_, F_, CW_, B_>;                                    \
+        which = ID_;                                                                  \
+    }
+    PICK(8, true, 8, 8, 0) PICK(16, true, 8, 8, 1) PICK(32, true, 8, 8, 2)
+    PICK(8, false, 8, 8, 3) PICK(16, false, 8, 8, 4) PICK(32, false, 8, 8, 5)
+    PICK(32, true, 8, 16, 6) PICK(32, true, 8, 4, 7)
+    PICK(8, true, 16, 8, 8) PICK(16, true, 16, 8, 9) PICK(16, true, 16, 4, 10) PICK(16, true, 16, 16, 11)
+    PICK(8, false, 16, 8, 12) PICK(16, false, 16, 8, 13)
+#undef PICK
+    if (!kern) {  // unsupported experimental combination: fall back to the default variant family
+        const int b = 8;
+        (void)b;
+        if (p.CW == 16) {
+            kern = full ? (Rt == 8 ? pass_fused_kernel<8, true, 16, 8> : pass_fused_kernel<16, true, 16, 8>)
+                        : (Rt == 8 ? pass_fused_kernel<8, false, 16, 8> : pass_fused_kernel<16, false, 16, 8>);
+            which = full ? (Rt == 8 ? 8 : 9) : (Rt == 8 ? 12 : 13);
+        } else {
+            kern = full ? (Rt == 8 ? pass_fused_kernel<8, true, 8, 8> : Rt == 16 ? pass_fused_kernel<16, true, 8, 8> : pass_fused_kernel<32, true, 8, 8>)
+                        : (Rt == 8 ? pass_fused_kernel<8, false, 8, 8> : Rt == 16 ? pass_fused_kernel<16, false, 8, 8> : pass_fused_kernel<32, false, 8, 8>);
+            which = (Rt == 8 ? 0 : Rt == 16 ? 1 : 2) + (full ? 0 : 3);
+        }
+    }
+    static size_t attrSet[16] = {0};
+    if (attrSet[which] < smem) {
+        MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attrSet[which] = smem;
     }
     MBAR_CUDA(cudaEventRecord(ctx->evA, ctx->stream));
-    kern<<<(unsigned)grid, FUSED_THREADS, smem, ctx->stream>>>(p);
+    kern<<<(unsigned)grid, p.CW * 32, smem, ctx->stream>>>(p);
     MBAR_CUDA(cudaEventRecord(ctx->evB, ctx->stream));
     ctx->launches++;
     ctx->passes++;
