@@ -80,7 +80,9 @@ __global__ void sci_epilogue_kernel(const double* __restrict__ out, double* __re
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         if (Nk[k] > 0.0) {
             const double fo = f[k];
-            const double fn = fo - log(out[k]) - s_f0;
+            // an underflowed S_k (linear-domain sums) poisons the result so the host redoes the
+            // iteration with the log-domain path
+            const double fn = (out[k] > 1e-280) ? fo - log(out[k]) - s_f0 : NAN;
             f[k] = fn;
             c[k] = fn + log(Nk[k]) - mid;
             if (k != first) {
@@ -130,20 +132,20 @@ static int run_pass(mbar_b200_ctx* c, const double* f, PassWant want) {
     const PassLayout lay{K};
     const bool needUnsampled = want.unsampled && (int)c->active.size() < K;
     const bool wantL = want.L || want.G;
+    // attempt 0: fused (if applicable) | 1: generic, linear sums | 2: generic, log-domain sums for
+    // every state (the reference's second logsumexp, mbar_solvers.py:240): taken when a sampled
+    // state's S_k underflows, i.e. f_k is hundreds of kT away from self-consistency.
     bool fused = false;
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int attempt = 0; attempt < 3; ++attempt) {
         fused = false;
+        const bool logAll = (attempt == 2);
         if (attempt == 0 && c->kernelChoice != MBAR_B200_KERNEL_GENERIC && !needUnsampled)
             MBAR_TRY(launch_pass_fused(c, f, wantL, &fused));
-        if (!fused) {
-            MBAR_REQUIRE(c->kernelChoice != MBAR_B200_KERNEL_FUSED || attempt == 1 || needUnsampled,
-                         MBAR_B200_ERR_INVALID,
-                         "fused kernel forced but not applicable (K=%d > 256 or spread of f_k too large)", K);
-            MBAR_TRY(launch_pass_generic(c, f, wantL));
-        }
+        if (attempt == 0 && !fused) continue;
+        if (!fused) MBAR_TRY(launch_pass_generic(c, f, wantL, logAll));
         // S | sumL | flag are sums over samples -> one all-reduce
         MBAR_TRY(comm_allreduce(c, c->d_out, K + 2, 0));
-        if (needUnsampled && c->comm && c->nranks > 1) {
+        if ((needUnsampled || logAll) && c->comm && c->nranks > 1) {
             double* mx = c->d_scratch;
             double* sc = c->d_scratch + K;
             MBAR_CUDA(cudaMemcpyAsync(mx, c->d_out + lay.logS(), K * sizeof(double),
@@ -160,8 +162,19 @@ static int run_pass(mbar_b200_ctx* c, const double* f, PassWant want) {
         c->d2hBytes += (int64_t)lay.size(false) * 8;
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->evA, c->evB) == cudaSuccess) c->lastPassMs = ms;
-        if (!(fused && c->h_out[lay.flag()] != 0.0)) break;
-        // the fused kernel's range assumption failed on some sample: redo with the generic kernel
+        if (fused && c->h_out[lay.flag()] != 0.0) continue;   // range assumption failed on a sample
+        if (logAll) {
+            for (int k : c->active) c->h_out[lay.S() + k] = std::exp(c->h_out[lay.logS() + k]);
+            break;
+        }
+        bool underflow = false;
+        for (int k : c->active) {
+            const double S = c->h_out[lay.S() + k];
+            if (!(S > 1e-280)) underflow = true;
+            c->h_out[lay.logS() + k] = std::log(S);
+        }
+        if (!underflow) break;
+        if (attempt == 0) ++attempt;   // skip the linear generic pass: it would underflow the same way
     }
     if (want.G) {
         MBAR_TRY(launch_hessian(c, f));
@@ -254,10 +267,7 @@ int mbar_b200_self_consistent_update(mbar_b200_ctx* c, const double* f, double* 
     MBAR_TRY(run_pass(c, f, w));
     const PassLayout lay{c->K};
     for (int k = 0; k < c->K; ++k) {
-        if (c->h_Nk[k] > 0)
-            f_out[k] = f[k] - std::log(c->h_out[lay.S() + k]);
-        else
-            f_out[k] = f[k] - c->h_out[lay.logS() + k];
+        f_out[k] = f[k] - c->h_out[lay.logS() + k];
     }
     return MBAR_B200_OK;
 }
@@ -348,6 +358,7 @@ int mbar_b200_solve_sci(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter
                         mbar_b200_solve_result* res) {
     MBAR_REQUIRE(c && f, MBAR_B200_ERR_INVALID, "NULL argument");
     const int K = c->K;
+    const PassLayout lay{K};
     std::vector<double> cur(f, f + K), nxt(K);
     mbar_b200_solve_result r{};
     cudaEvent_t e0, e1;
@@ -361,7 +372,7 @@ int mbar_b200_solve_sci(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter
         if (rc != MBAR_B200_OK) break;
         r.passes++;
         nxt = cur;
-        for (int k : c->active) nxt[k] = cur[k] - std::log(c->h_out[k]);
+        for (int k : c->active) nxt[k] = cur[k] - c->h_out[lay.logS() + k];
         const double shift = nxt[g0];
         for (int k : c->active) nxt[k] -= shift;
         r.max_delta = rel_delta(c, nxt, cur, tol);
@@ -430,7 +441,7 @@ int mbar_b200_solve_adaptive(mbar_b200_ctx* c, double* f, double tol, int32_t ma
         r.hessian_passes++;
         grad_from_out(g);
         f_sci = cur;
-        for (int k : c->active) f_sci[k] = cur[k] - std::log(c->h_out[k]);
+        for (int k : c->active) f_sci[k] = cur[k] - c->h_out[lay.logS() + k];
         {
             const double s0 = f_sci[g0];
             for (int k : c->active) f_sci[k] -= s0;
@@ -540,8 +551,9 @@ int mbar_b200_sci_iterate(mbar_b200_ctx* c, double* f, int32_t iters) {
         std::vector<double> cur(f, f + K);
         for (int it = 0; it < iters; ++it) {
             MBAR_TRY(run_pass(c, cur.data(), PassWant{}));
-            const double s0 = cur[c->firstActive] - std::log(c->h_out[c->firstActive]);
-            for (int k : c->active) cur[k] = cur[k] - std::log(c->h_out[k]) - s0;
+            const PassLayout lay2{K};
+            const double s0 = cur[c->firstActive] - c->h_out[lay2.logS() + c->firstActive];
+            for (int k : c->active) cur[k] = cur[k] - c->h_out[lay2.logS() + k] - s0;
         }
         std::memcpy(f, cur.data(), K * sizeof(double));
         return MBAR_B200_OK;
@@ -566,8 +578,20 @@ int mbar_b200_sci_iterate(mbar_b200_ctx* c, double* f, int32_t iters) {
     c->d2hBytes += K * 8 + lay.size(false) * 8;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->evA, c->evB) == cudaSuccess) c->lastPassMs = ms;
-    MBAR_REQUIRE(iters == 0 || c->h_out[lay.flag()] == 0.0, MBAR_B200_ERR_RANGE,
-                 "fused kernel range check failed during device-resident iteration");
+    if (iters > 0 && c->h_out[lay.flag()] != 0.0) c->h_f[4 * K + c->firstActive] = NAN;  // force the robust redo
+    bool finite = true;
+    for (int k : c->active) finite = finite && std::isfinite(c->h_f[4 * K + k]);
+    if (!finite) {
+        // some S_k underflowed in the linear-domain fused kernel: redo with the robust stepped path
+        std::vector<double> cur(f, f + K);
+        for (int it = 0; it < iters; ++it) {
+            MBAR_TRY(run_pass(c, cur.data(), PassWant{}));
+            const double s0 = cur[c->firstActive] - c->h_out[lay.logS() + c->firstActive];
+            for (int k : c->active) cur[k] = cur[k] - c->h_out[lay.logS() + k] - s0;
+        }
+        std::memcpy(f, cur.data(), K * sizeof(double));
+        return MBAR_B200_OK;
+    }
     for (int k = 0; k < K; ++k)
         if (c->h_Nk[k] > 0) f[k] = c->h_f[4 * K + k];
     return MBAR_B200_OK;

@@ -76,6 +76,7 @@ struct mbar_b200_ctx {
     double* d_c = nullptr;          // [2][K] c_k = f_k + log N_k - mid (fused) | f_k (row K..2K)
     double* d_Nk = nullptr;         // [K]
     unsigned long long* d_rowmask = nullptr;  // [ceil(K/64)] bit per sampled state
+    unsigned long long* d_zeromask = nullptr; // same size, all zero (log-domain for every row)
     double* d_partial = nullptr;    // [MAX_GRID][K+2] per-CTA partials
     double* d_out = nullptr;        // PassLayout packed result (with G)
     double* h_out = nullptr;        // pinned mirror of d_out
@@ -124,7 +125,7 @@ struct FusedParams {
 // ---- host-side helpers implemented across the .cu files ----
 int retile_chunk(mbar_b200_ctx* ctx, const double* d_rowmajor, int64_t ldCols, int64_t tile0,
                  int64_t nTilesChunk, int64_t validCols, cudaStream_t s);
-int launch_pass_generic(mbar_b200_ctx* ctx, const double* h_f, bool wantL);
+int launch_pass_generic(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool logAll);
 int launch_pass_fused(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool* usedOut);
 int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams* out, bool* ok);
 int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p);

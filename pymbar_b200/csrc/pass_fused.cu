@@ -49,11 +49,10 @@ __device__ __forceinline__ double lds_f64(const double* p) {
 // are issued right after the rounding step (5 polynomial stages ahead of their use) and the
 // energies of the NEXT batch are fetched before this batch's polynomial (volatile loads keep their
 // program position; two consumer warps per scheduler cannot hide ~30-cycle LDS otherwise).
-template <int B, bool PREFETCH>
-__device__ __forceinline__ void exp_batch(const double (&cu)[B], const double (&uu)[B],
-                                          int tabHi, int tabLo, double (&e)[B],
-                                          const double* nextC, const double* nextU,
-                                          double (&cn)[B], double (&un)[B]) {
+template <int R, int B, int R0, bool PREFETCH>
+__device__ __forceinline__ void exp_batch(const double (&cu)[B], const double (&uu)[B], int tabHi, int tabLo,
+                                          double (&e)[R], double& Dp, const double* nextC,
+                                          const double* nextU, double (&cn)[B], double (&un)[B]) {
     double t[B], r[B], pl[B], T[B];
 #pragma unroll
     for (int i = 0; i < B; ++i) {
@@ -92,7 +91,36 @@ __device__ __forceinline__ void exp_batch(const double (&cu)[B], const double (&
 #pragma unroll
     for (int i = 0; i < B; ++i) pl[i] = pl[i] * r[i];
 #pragma unroll
-    for (int i = 0; i < B; ++i) e[i] = scale2(fma(T[i], pl[i], T[i]), __double2loint(t[i]) >> 5);
+    for (int i = 0; i < B; ++i) {
+        e[R0 + i] = scale2(fma(T[i], pl[i], T[i]), __double2loint(t[i]) >> 5);
+        Dp += e[R0 + i];
+    }
+}
+
+// All R rows of a thread in batches of B with two alternating input register sets (no copies).
+template <int R, int B, int R0>
+__device__ __forceinline__ void exp_rows(double (&cA)[B], double (&uA)[B], double (&cB)[B], double (&uB)[B],
+                                         int tabHi, int tabLo, double (&e)[R], double& Dp,
+                                         const double* cbase, const double* ubase) {
+    if constexpr (R0 + B < R) {
+        exp_batch<R, B, R0, true>(cA, uA, tabHi, tabLo, e, Dp, cbase + R0 + B, ubase + (R0 + B) * TILE_N, cB, uB);
+        exp_rows<R, B, R0 + B>(cB, uB, cA, uA, tabHi, tabLo, e, Dp, cbase, ubase);
+    } else {
+        exp_batch<R, B, R0, false>(cA, uA, tabHi, tabLo, e, Dp, nullptr, nullptr, cB, uB);
+    }
+}
+
+// sum_n log D_n without a log per sample: D = m * 2^x with m in [1, 2); the exponents are summed as
+// integers and the mantissas multiplied (renormalised by the caller before they can overflow).
+__device__ __forceinline__ void logprod_push(double D, double& mprod, int& esum) {
+    const int hi = __double2hiint(D);
+    esum += (hi >> 20) - 1023;
+    mprod *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(D));
+}
+__device__ __forceinline__ void logprod_renorm(double& mprod, int& esum) {
+    const int hi = __double2hiint(mprod);
+    esum += (hi >> 20) - 1023;
+    mprod = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(mprod));
 }
 
 template <int R, bool FULL, int CW, int BATCH>
@@ -161,6 +189,8 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
         }
         int par = 0;
         int it = 0;
+        double mprod = 1.0;   // running product of the mantissas of D_n (see logprod_push)
+        int esum = 0, npush = 0;
         const int tabHi = __double2hiint(MBAR_EXP_TABLE[lane]);
         const int tabLo = __double2loint(MBAR_EXP_TABLE[lane]);
         for (int64_t s = blockIdx.x; s < p.nStages; s += gridDim.x, ++it) {
@@ -181,30 +211,13 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                 if (FULL) {
                     // every warp owns exactly R sampled rows: branch-free, 8 rows at a time
                     constexpr int B = R < BATCH ? R : BATCH;
-                    double cu[B], uu[B];
+                    double cA[B], uA[B], cB[B], uB[B];
 #pragma unroll
                     for (int i = 0; i < B; ++i) {
-                        uu[i] = lds_f64(tp + i * TILE_N);
-                        cu[i] = lds_f64(c_s + k0 + i);
+                        uA[i] = lds_f64(tp + i * TILE_N);
+                        cA[i] = lds_f64(c_s + k0 + i);
                     }
-
-#pragma unroll
-                    for (int r0 = 0; r0 < R; r0 += B) {
-                        double eb[B], cn[B], un[B];
-                        if (r0 + B < R)
-                            exp_batch<B, true>(cu, uu, tabHi, tabLo, eb, c_s + k0 + r0 + B, tp + (r0 + B) * TILE_N, cn, un);
-                        else
-                            exp_batch<B, false>(cu, uu, tabHi, tabLo, eb, nullptr, nullptr, cn, un);
-#pragma unroll
-                        for (int i = 0; i < B; ++i) {
-                            e[r0 + i] = eb[i];
-                            Dp += eb[i];
-                            if (r0 + B < R) {
-                                cu[i] = cn[i];
-                                uu[i] = un[i];
-                            }
-                        }
-                    }
+                    exp_rows<R, B, 0>(cA, uA, cB, uB, tabHi, tabLo, e, Dp, c_s + k0, tp);
                 } else {
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
@@ -232,9 +245,11 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
 #pragma unroll
                 for (int r = 0; r < R; ++r) acc[r] = fma(e[r], invD, acc[r]);
                 if (w == 0) {
-                    const double logD = log(D);
-                    if (valid) sumL += logD;
-                    if (p.Lout) p.Lout[tile * TILE_N + lane] = logD + p.mid;
+                    if (valid) {
+                        logprod_push(D, mprod, esum);
+                        if ((++npush & 255) == 0) logprod_renorm(mprod, esum);
+                    }
+                    if (p.Lout) p.Lout[tile * TILE_N + lane] = log(D) + p.mid;
                 }
             }
             __syncwarp();
@@ -246,6 +261,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
             const double t = warp_sum(acc[r]);
             if (lane == 0 && r < p.Rw && k0 + r < K) sred[g * K + k0 + r] = t;
         }
+        sumL = (double)esum * 0.693147180559945309417232 + log(mprod);
         sumL = warp_sum(sumL);
         bad = __any_sync(0xffffffffu, bad);
         if (lane == 0) {

@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256)
 pass_generic_kernel(const double* __restrict__ u, int K, int64_t N, int64_t nTiles,
                     const double* __restrict__ c, const double* __restrict__ f,
                     const unsigned long long* __restrict__ rowmask,
+                    const unsigned long long* __restrict__ linmask,
                     const double* __restrict__ Nk, double* __restrict__ partial,
                     double* __restrict__ out, unsigned int* __restrict__ ticket,
                     double* __restrict__ Lout, int warpsPerCta) {
@@ -40,7 +41,7 @@ pass_generic_kernel(const double* __restrict__ u, int K, int64_t N, int64_t nTil
     if (threadIdx.x < 32) tab[threadIdx.x] = MBAR_EXP_TABLE[threadIdx.x];
     for (int i = threadIdx.x; i < W * K; i += blockDim.x) {
         const int k = i % K;
-        const bool act = row_active(rowmask, k);
+        const bool act = row_active(linmask, k);
         acc[2 * i] = act ? 0.0 : -INFINITY;
         acc[2 * i + 1] = 0.0;
     }
@@ -68,7 +69,7 @@ pass_generic_kernel(const double* __restrict__ u, int K, int64_t N, int64_t nTil
                 const int k = k0 + kk;
                 const double uv = tp[(int64_t)k * TILE_N];
                 double val;
-                if (row_active(rowmask, k))
+                if (row_active(linmask, k))
                     val = valid ? exp_fast(fmax(__ldg(c + k) - uv - Lp, -800.0), tab) : 0.0;
                 else
                     val = (kNeedUnsampled && valid) ? (__ldg(f + k) - uv - Lp) : -INFINITY;
@@ -77,7 +78,7 @@ pass_generic_kernel(const double* __restrict__ u, int K, int64_t N, int64_t nTil
             __syncwarp();
             const int k = k0 + lane;
             if (k < K) {
-                if (row_active(rowmask, k)) {
+                if (row_active(linmask, k)) {
                     double s = 0.0;
 #pragma unroll 8
                     for (int j = 0; j < 32; ++j) s += T[lane * 33 + j];
@@ -116,7 +117,7 @@ pass_generic_kernel(const double* __restrict__ u, int K, int64_t N, int64_t nTil
     // merge the warps of this CTA -> partial[cta][0..K) = S or M, [K..2K) = A, [2K] = sumL
     double* P = partial + (size_t)blockIdx.x * (3 * (size_t)K + 2);
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        if (row_active(rowmask, k)) {
+        if (row_active(linmask, k)) {
             double s = 0.0;
             for (int w = 0; w < W; ++w) s += acc[((size_t)w * K + k) * 2];
             P[k] = s;
@@ -154,7 +155,7 @@ pass_generic_kernel(const double* __restrict__ u, int K, int64_t N, int64_t nTil
     const PassLayout lay{K};
     const size_t stride = 3 * (size_t)K + 2;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        if (row_active(rowmask, k)) {
+        if (row_active(linmask, k)) {
             double s = 0.0;
             for (unsigned b = 0; b < gridDim.x; ++b) s += partial[b * stride + k];
             out[lay.S() + k] = s / Nk[k];
@@ -183,7 +184,7 @@ pass_generic_kernel(const double* __restrict__ u, int K, int64_t N, int64_t nTil
     }
 }
 
-int launch_pass_generic(mbar_b200_ctx* ctx, const double* h_f, bool wantL) {
+int launch_pass_generic(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool logAll) {
     const int K = ctx->K;
     // c (sampled) and f (all) to the device
     for (int k = 0; k < K; ++k) {
@@ -199,7 +200,7 @@ int launch_pass_generic(mbar_b200_ctx* ctx, const double* h_f, bool wantL) {
     if (W > 8) W = 8;
     MBAR_REQUIRE(W >= 1, MBAR_B200_ERR_INVALID, "K=%d too large for the generic kernel", K);
     const size_t smem = 256 + (size_t)W * perWarp;
-    const bool needUnsampled = (int)ctx->active.size() < K;
+    const bool needUnsampled = logAll || (int)ctx->active.size() < K;
     if (wantL && !ctx->d_L)
         MBAR_CUDA(cudaMalloc((void**)&ctx->d_L, (size_t)ctx->nTiles * TILE_N * sizeof(double)));
     int64_t grid = (ctx->nTiles + W - 1) / W;
@@ -210,7 +211,8 @@ int launch_pass_generic(mbar_b200_ctx* ctx, const double* h_f, bool wantL) {
     MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MBAR_CUDA(cudaEventRecord(ctx->evA, ctx->stream));
     kern<<<(unsigned)grid, W * 32, smem, ctx->stream>>>(ctx->d_u, K, ctx->N, ctx->nTiles, ctx->d_c,
-                                                       ctx->d_c + K, ctx->d_rowmask, ctx->d_Nk,
+                                                       ctx->d_c + K, ctx->d_rowmask,
+                                                       logAll ? ctx->d_zeromask : ctx->d_rowmask, ctx->d_Nk,
                                                        ctx->d_partial, ctx->d_out, ctx->d_ticket,
                                                        wantL ? ctx->d_L : nullptr, W);
     MBAR_CUDA(cudaEventRecord(ctx->evB, ctx->stream));

@@ -150,6 +150,13 @@ class DeviceProblem:
         check(self._lib.mbar_b200_comm_init(self._h, int(nranks), int(rank), buf))
 
     # ---- the pass and the reference primitives ----------------------------------------------------
+    def _bad(self, f):
+        """The reference propagates NaN through its primitives; the C ABI
+        reports ERR_RANGE instead.  Mirror the reference for optimiser trial points that left the
+        representable range: non-finite (or > 1e6 in magnitude) f_k on a sampled state -> NaNs."""
+        c = f[self.N_k > 0]
+        return not np.all(np.isfinite(c)) or np.max(np.abs(c)) > 9.0e5
+
     def streaming_pass(self, f_k, want_G=False):
         f = _f64(f_k, self.K)
         S = np.empty(self.K)
@@ -161,18 +168,24 @@ class DeviceProblem:
 
     def self_consistent_update(self, f_k):
         f = _f64(f_k, self.K)
+        if self._bad(f):
+            return np.full(self.K, np.nan)
         out = np.empty(self.K)
         check(self._lib.mbar_b200_self_consistent_update(self._h, _dptr(f), _dptr(out)))
         return out
 
     def gradient(self, f_k):
         f = _f64(f_k, self.K)
+        if self._bad(f):
+            return np.full(self.K, np.nan)
         out = np.empty(self.K)
         check(self._lib.mbar_b200_gradient(self._h, _dptr(f), _dptr(out)))
         return out
 
     def objective_and_gradient(self, f_k):
         f = _f64(f_k, self.K)
+        if self._bad(f):
+            return np.nan, np.full(self.K, np.nan)
         g = np.empty(self.K)
         obj = C.c_double(0)
         check(self._lib.mbar_b200_objective_and_gradient(self._h, _dptr(f), C.byref(obj), _dptr(g)))
@@ -180,12 +193,16 @@ class DeviceProblem:
 
     def objective(self, f_k):
         f = _f64(f_k, self.K)
+        if self._bad(f):
+            return np.nan
         obj = C.c_double(0)
         check(self._lib.mbar_b200_objective_and_gradient(self._h, _dptr(f), C.byref(obj), None))
         return obj.value
 
     def hessian(self, f_k):
         f = _f64(f_k, self.K)
+        if self._bad(f):
+            return np.full((self.K, self.K), np.nan)
         H = np.empty((self.K, self.K))
         check(self._lib.mbar_b200_hessian(self._h, _dptr(f), _dptr(H)))
         return H

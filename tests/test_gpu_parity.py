@@ -148,9 +148,10 @@ def test_errors(lib):
         f = np.zeros(len(N))
         ref = orc.self_consistent_update(u, N, f)
         np.testing.assert_allclose(p.self_consistent_update(f), ref, atol=1e-10)
-        with pytest.raises(MbarB200Error) as e2:
-            p.gradient(np.full(len(N), 1e9))
+        with pytest.raises(MbarB200Error) as e2:          # raw C ABI: explicit range error
+            p.streaming_pass(np.full(len(N), 1e9))
         assert e2.value.status == -6
+        assert np.all(np.isnan(p.gradient(np.full(len(N), np.nan))))   # mirror: NaN in, NaN out
     with pytest.raises(lib.ParameterError):
         lib.mbar_solvers.solve_mbar_once(z["u_kn"], N, np.zeros(len(N)), method="no-such-method")
     with pytest.raises(TypeError):
@@ -164,3 +165,26 @@ def test_wide_f_spread_falls_back(lib):
     f = np.linspace(0, 3000, len(N))
     with lib.DeviceProblem(u, N) as p:
         np.testing.assert_allclose(p.self_consistent_update(f), orc.self_consistent_update(u, N, f), atol=1e-9)
+
+
+def test_large_energy_offsets(lib):
+    """States whose energies carry large constant offsets (true f_k thousands of kT from the
+    starting guess): S_k underflows in linear arithmetic, the reference's logsumexp does not."""
+    z = _cases.load("small_osc_8x40")
+    N = z["N_k"].astype(float)
+    K = len(N)
+    off = np.linspace(0, 5000, K)
+    u = z["u_kn"] + off[:, None]
+    f0 = np.zeros(K)
+    with lib.DeviceProblem(u, N) as p:
+        np.testing.assert_allclose(p.self_consistent_update(f0), orc.self_consistent_update(u, N, f0), atol=1e-8)
+        np.testing.assert_allclose(p.gradient(f0), orc.mbar_gradient(u, N, f0), rtol=1e-9, atol=1e-7)
+        f_dev = p.sci_iterate(f0, 3)
+        f_host = f0.copy()
+        for _ in range(3):
+            nxt = orc.self_consistent_update(u, N, f_host)
+            f_host = nxt - nxt[0]
+        np.testing.assert_allclose(f_dev, f_host, atol=1e-8)
+    f = lib.mbar_solvers.solve_mbar_for_all_states(u, z["N_k"], np.zeros(K), np.arange(K),
+                                                   lib.mbar_solvers.DEFAULT_SOLVER_PROTOCOL)
+    np.testing.assert_allclose(f - off, z["fk_default"], atol=1e-7)
