@@ -148,6 +148,10 @@ int mbar_b200_solve_adaptive(mbar_b200_ctx* ctx, double* f_inout, double tol, in
 /* Run exactly `iters` self-consistent passes back to back with no host round trip (bench). */
 int mbar_b200_sci_iterate(mbar_b200_ctx* ctx, double* f_inout, int32_t iters);
 
+/* CUDA-event timing of the last mbar_b200_sci_iterate on the context's stream: whole loop (pass +
+ * all-reduce + K-vector epilogue per iteration) and the sum of the pass-kernel launch durations. */
+int mbar_b200_last_loop_ms(mbar_b200_ctx* ctx, double* total_ms, double* kernel_ms_sum, int32_t* iters);
+
 /* ---- one-shot, host-buffer entry (what a binding without residency would call) --------------- */
 /* self_consistent_update on host buffers: upload u_kn, one pass, f_out — copies inside the call. */
 int mbar_b200_self_consistent_update_host(int device, int32_t K, int64_t N, const double* u_host,

@@ -65,6 +65,7 @@ SIGNATURES = {
     "mbar_b200_solve_adaptive": (C.c_int, [_ctx, _dp, C.c_double, C.c_int32, C.c_int32, C.c_double,
                                            C.POINTER(SolveResult)]),
     "mbar_b200_sci_iterate": (C.c_int, [_ctx, _dp, C.c_int32]),
+    "mbar_b200_last_loop_ms": (C.c_int, [_ctx, _dp, _dp, C.POINTER(C.c_int32)]),
     "mbar_b200_self_consistent_update_host": (C.c_int, [C.c_int, C.c_int32, C.c_int64, C.c_void_p, C.c_int64,
                                                         _dp, _dp, _dp]),
     "mbar_b200_comm_unique_id": (C.c_int, [C.c_void_p]),

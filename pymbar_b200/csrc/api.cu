@@ -562,12 +562,43 @@ int mbar_b200_sci_iterate(mbar_b200_ctx* c, double* f, int32_t iters) {
     MBAR_CUDA(cudaMemcpyAsync(c->d_f, c->h_f + 4 * K, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     c->h2dBytes += K * 8;
     const int threads = K >= 256 ? 256 : ((K + 31) / 32) * 32;
+    // per-launch CUDA events of the pass kernel (bench: average launch duration over the loop)
+    std::vector<cudaEvent_t> ev;
+    const bool perLaunch = c->timePasses && iters > 0 && iters <= 4096;
+    if (perLaunch) {
+        ev.resize(2 * (size_t)iters);
+        for (auto& e : ev) MBAR_CUDA(cudaEventCreate(&e));
+    }
+    cudaEvent_t l0, l1;
+    MBAR_CUDA(cudaEventCreate(&l0));
+    MBAR_CUDA(cudaEventCreate(&l1));
+    MBAR_CUDA(cudaEventRecord(l0, c->stream));
     for (int it = 0; it < iters; ++it) {
+        if (perLaunch) MBAR_CUDA(cudaEventRecord(ev[2 * it], c->stream));
         MBAR_TRY(fused_enqueue(c, p));
+        if (perLaunch) MBAR_CUDA(cudaEventRecord(ev[2 * it + 1], c->stream));
         MBAR_TRY(comm_allreduce(c, c->d_out, K + 2, 0));
         sci_epilogue_kernel<<<1, threads, 0, c->stream>>>(c->d_out, c->d_f, c->d_c, c->d_Nk, K, c->firstActive,
                                                          p.mid, c->d_scratch);
         c->launches++;
+    }
+    MBAR_CUDA(cudaEventRecord(l1, c->stream));
+    MBAR_CUDA(cudaEventSynchronize(l1));
+    {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, l0, l1);
+        c->lastLoopMs = ms;
+        double ksum = 0.0;
+        for (int it = 0; perLaunch && it < iters; ++it) {
+            float k = 0.f;
+            cudaEventElapsedTime(&k, ev[2 * it], ev[2 * it + 1]);
+            ksum += k;
+        }
+        c->lastLoopKernelMs = ksum;
+        c->lastLoopIters = iters;
+        for (auto& e : ev) cudaEventDestroy(e);
+        cudaEventDestroy(l0);
+        cudaEventDestroy(l1);
     }
     MBAR_CUDA(cudaGetLastError());
     MBAR_CUDA(cudaMemcpyAsync(c->h_f + 4 * K, c->d_f, K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -594,6 +625,14 @@ int mbar_b200_sci_iterate(mbar_b200_ctx* c, double* f, int32_t iters) {
     }
     for (int k = 0; k < K; ++k)
         if (c->h_Nk[k] > 0) f[k] = c->h_f[4 * K + k];
+    return MBAR_B200_OK;
+}
+
+int mbar_b200_last_loop_ms(mbar_b200_ctx* c, double* total_ms, double* kernel_ms_sum, int32_t* iters) {
+    MBAR_REQUIRE(c, MBAR_B200_ERR_INVALID, "ctx is NULL");
+    if (total_ms) *total_ms = c->lastLoopMs;
+    if (kernel_ms_sum) *kernel_ms_sum = c->lastLoopKernelMs;
+    if (iters) *iters = c->lastLoopIters;
     return MBAR_B200_OK;
 }
 

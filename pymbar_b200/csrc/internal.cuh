@@ -102,6 +102,8 @@ struct mbar_b200_ctx {
     // counters
     int64_t launches = 0, passes = 0, h2dBytes = 0, d2hBytes = 0;
     double lastPassMs = 0.0;
+    double lastLoopMs = 0.0, lastLoopKernelMs = 0.0;
+    int lastLoopIters = 0;
     bool timePasses = true;
 };
 

@@ -138,6 +138,11 @@ class DeviceProblem:
         check(self._lib.mbar_b200_last_pass_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def last_loop_ms(self):
+        tot, ker, it = C.c_double(0), C.c_double(0), C.c_int32(0)
+        check(self._lib.mbar_b200_last_loop_ms(self._h, C.byref(tot), C.byref(ker), C.byref(it)))
+        return dict(total_ms=tot.value, kernel_ms_sum=ker.value, iters=it.value)
+
     # ---- communicator -------------------------------------------------------------------------
     @staticmethod
     def comm_unique_id():
