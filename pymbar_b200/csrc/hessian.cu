@@ -3,22 +3,28 @@
 // Reference being replaced: mbar_hessian (mbar_solvers.py:395-411): W = exp(f - u^T - L) [N,K];
 // H = -( (W^T W) * N N^T - diag(N_k sum_n W_nk) ).  With  w_kn = N_k W_nk = exp(c_k - u'_kn - L'_n):
 //   H_ij = delta_ij N_i S_i - Ghat_ij,   Ghat_ij = sum_n w_in w_jn.
-// This is the only compute-bound piece of the path (2 K^2 N flop vs 8 K N bytes); there is no fp64
-// tcgen05 MMA, so it uses the legacy warp-level DMMA (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4).
+// This is the only compute-bound piece of the path (2 K^2 N flop vs 8 K N bytes).  There is no fp64
+// tcgen05 MMA, so it uses the warp-level DMMA (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4), which on B200
+// runs on its own tensor sub-pipe at 64 MAC/clk/SM (measured: 16 cycles per instruction per scheduler)
+// — the same rate as the vector fp64 pipe, but concurrently with it.
 //
-// Decomposition: the lower block-triangle of Ghat in 128 x 128 blocks; a CTA owns one block pair
-// (bi >= bj) and one contiguous chunk of tiles, recomputes the two 128 x 32 weight panels per tile
-// from u' and the stored L'_n (one exp per entry), stages them in shared memory (stride 36: the
-// 8-row x 4-sample DMMA fragments are bank-conflict free) and accumulates 64 x 32 per warp in
-// registers.  Per-chunk partial blocks are reduced by a second kernel in chunk order (deterministic).
+// Decomposition: lower block-triangle of Ghat in 128 x 128 blocks; a CTA owns one block pair
+// (bi >= bj) and one contiguous chunk of tiles.  Per tile:
+//   * thread 0 streams the two 128 x 32 energy panels (32 KB contiguous each in the tile-major
+//     layout) into a 3-deep shared-memory ring with cp.async.bulk + mbarriers;
+//   * phase 1: every warp turns 16 rows of each panel into weights IN PLACE (one exp per entry,
+//     stored with an XOR swizzle so that the 8-row x 4-sample DMMA fragments are conflict free);
+//   * one __syncthreads; phase 2: 8 warps x (64 x 32) register tiles, 32 DMMA per 4-sample step.
+// Per-chunk partial blocks are reduced by a second kernel in chunk order (deterministic).
 #include <cmath>
 
 #include "internal.cuh"
 
 namespace mbar {
 
-constexpr int HB = 128;       // block edge
-constexpr int HSTRIDE = 36;   // smem row stride in doubles (32 samples + 4 pad)
+constexpr int HB = 128;                    // block edge
+constexpr int HNS = 3;                     // ring depth
+constexpr uint32_t HPANEL = HB * TILE_N * 8;   // 32 KB
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -30,19 +36,47 @@ __global__ void __launch_bounds__(256, 1)
 hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
                const double* __restrict__ c, const unsigned long long* __restrict__ rowmask, int K,
                int64_t N, int64_t nTiles, int nChunks, double* __restrict__ Gpart) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* tab = reinterpret_cast<double*>(smem_raw);           // [32]
-    double* panels = tab + 32;                                   // [2 buf][2 panel][HB][HSTRIDE]
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* tab = reinterpret_cast<double*>(smem_raw);                      // [32]
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(tab + 32);             // [HNS]
+    uint64_t* bar_empty = bar_full + 4;                                     // [HNS]
+    unsigned char* ring = smem_raw + 512;                                   // [HNS][2][HPANEL]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < 32) tab[threadIdx.x] = MBAR_EXP_TABLE[threadIdx.x];
 
-    // block pair from blockIdx.x: pairs enumerated (0,0),(1,0),(1,1),(2,0),...
-    int bi = 0, rem = blockIdx.x;
+    int bi = 0, rem = blockIdx.x;                 // pairs enumerated (0,0),(1,0),(1,1),(2,0),...
     while (rem > bi) { rem -= bi + 1; ++bi; }
     const int bj = rem;
     const bool diag = (bi == bj);
     const int chunk = blockIdx.y;
     const int64_t t0 = nTiles * chunk / nChunks, t1 = nTiles * (chunk + 1) / nChunks;
+    const int rowsI = min(HB, K - bi * HB), rowsJ = min(HB, K - bj * HB);
+    const uint32_t stageBytes = diag ? HPANEL : 2 * HPANEL;
+
+    if (threadIdx.x < 32) tab[threadIdx.x] = MBAR_EXP_TABLE[threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < HNS; ++i) {
+            mbar_init(smem_u32(&bar_full[i]), 1);
+            mbar_init(smem_u32(&bar_empty[i]), 8);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int it) {
+        const int64_t tile = t0 + it;
+        if (tile >= t1) return;
+        const int slot = it % HNS;
+        if (it >= HNS) mbar_wait(smem_u32(&bar_empty[slot]), ((it / HNS) - 1) & 1);
+        const uint32_t fb = smem_u32(&bar_full[slot]);
+        const uint32_t bytesI = (uint32_t)rowsI * TILE_N * 8, bytesJ = (uint32_t)rowsJ * TILE_N * 8;
+        mbar_arrive_expect_tx(fb, bytesI + (diag ? 0u : bytesJ));
+        const double* base = u + tile * (int64_t)K * TILE_N;
+        const uint32_t dst = smem_u32(ring + (size_t)slot * 2 * HPANEL);
+        bulk_g2s(dst, base + (int64_t)bi * HB * TILE_N, bytesI, fb);
+        if (!diag) bulk_g2s(dst + HPANEL, base + (int64_t)bj * HB * TILE_N, bytesJ, fb);
+    };
+    if (threadIdx.x == 0)
+        for (int i = 0; i < HNS - 1; ++i) issue(i);
 
     // phase-1 mapping: lane = sample, warp fills rows warp*16 .. +15 of each panel
     // phase-2 mapping: warp tile 64 (i) x 32 (j): wm = warp / 4 (0..1), wn = warp % 4 (0..3)
@@ -65,49 +99,66 @@ hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
         actI |= (uint32_t)ai << r;
         actJ |= (uint32_t)aj << r;
     }
-    __syncthreads();
+    // swizzled column of (row, n): n ^ ((row & 7) << 2); rows handled by this thread in phase 1 are
+    // warp*16 + r, so (row & 7) = r & 7.
+    const int fragCol = lane & 3, fragRow = lane >> 2;   // DMMA fragment coordinates of this lane
 
-    int buf = 0;
-    for (int64_t tile = t0; tile < t1; ++tile, buf ^= 1) {
-        double* Pi = panels + (size_t)buf * 2 * HB * HSTRIDE;
-        double* Pj = diag ? Pi : Pi + HB * HSTRIDE;
+    int it = 0;
+    double Lnext = (t0 < t1) ? Lp[t0 * TILE_N + lane] : 0.0;
+    for (int64_t tile = t0; tile < t1; ++tile, ++it) {
+        const int slot = it % HNS;
+        if (threadIdx.x == 0) issue(it + HNS - 1);
+        const double L = Lnext;
+        if (tile + 1 < t1) Lnext = Lp[(tile + 1) * TILE_N + lane];
         const bool valid = tile * TILE_N + lane < N;
-        const double L = Lp[tile * TILE_N + lane];
-        const double* tp = u + tile * (int64_t)K * TILE_N + lane;
+        mbar_wait(smem_u32(&bar_full[slot]), (it / HNS) & 1);
+        double* Pi = reinterpret_cast<double*>(ring + (size_t)slot * 2 * HPANEL);
+        double* Pj = diag ? Pi : Pi + HB * TILE_N;
+
+        // ---- phase 1: energies -> weights in place (read the 16 rows first, then write swizzled)
+        {
+            double v[16];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const int kl = warp * 16 + r;
-            double wv = 0.0;
-            if (valid && ((actI >> r) & 1u))
-                wv = exp_fast(fmax(cI[r] - tp[(int64_t)(bi * HB + kl) * TILE_N] - L, -800.0), tab);
-            Pi[kl * HSTRIDE + lane] = wv;
-        }
-        if (!diag) {
+            for (int r = 0; r < 16; ++r) v[r] = Pi[(warp * 16 + r) * TILE_N + lane];
+            __syncwarp();
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
-                const int kl = warp * 16 + r;
                 double wv = 0.0;
-                if (valid && ((actJ >> r) & 1u))
-                    wv = exp_fast(fmax(cJ[r] - tp[(int64_t)(bj * HB + kl) * TILE_N] - L, -800.0), tab);
-                Pj[kl * HSTRIDE + lane] = wv;
+                if (valid && ((actI >> r) & 1u)) wv = exp_fast(fmax(cI[r] - v[r] - L, -800.0), tab);
+                Pi[(warp * 16 + r) * TILE_N + (lane ^ ((r & 7) << 2))] = wv;
+            }
+            if (!diag) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) v[r] = Pj[(warp * 16 + r) * TILE_N + lane];
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    double wv = 0.0;
+                    if (valid && ((actJ >> r) & 1u)) wv = exp_fast(fmax(cJ[r] - v[r] - L, -800.0), tab);
+                    Pj[(warp * 16 + r) * TILE_N + (lane ^ ((r & 7) << 2))] = wv;
+                }
             }
         }
         __syncthreads();
-        const double* Ai = Pi + (wm * 64 + (lane >> 2)) * HSTRIDE + (lane & 3);
-        const double* Bj = Pj + (wn * 32 + (lane >> 2)) * HSTRIDE + (lane & 3);
+        // ---- phase 2: Ghat block += Pi Pj^T on the DMMA pipe
+        const double* Ai = Pi + (wm * 64 + fragRow) * TILE_N;
+        const double* Bj = Pj + (wn * 32 + fragRow) * TILE_N;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
+            const int col = ((ks ^ fragRow) << 2) + fragCol;      // (4 ks + fragCol) ^ (fragRow << 2)
             double a[8], b[4];
 #pragma unroll
-            for (int mt = 0; mt < 8; ++mt) a[mt] = Ai[mt * 8 * HSTRIDE + ks * 4];
+            for (int mt = 0; mt < 8; ++mt) a[mt] = Ai[mt * 8 * TILE_N + col];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) b[nt] = Bj[nt * 8 * HSTRIDE + ks * 4];
+            for (int nt = 0; nt < 4; ++nt) b[nt] = Bj[nt * 8 * TILE_N + col];
 #pragma unroll
             for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
         }
-        // no second barrier: the next tile writes the other buffer
+        fence_proxy_async_smem();   // the slot was written in place; the next writer is the TMA engine
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_empty[slot]));
     }
     // write this CTA's 128 x 128 partial block: Gpart[chunk][pair][128][128]
     const int nPairs = gridDim.x;
@@ -157,8 +208,12 @@ int launch_hessian(mbar_b200_ctx* ctx, const double* h_f) {
     if ((int64_t)nChunks > ctx->nTiles) nChunks = (int)ctx->nTiles;
     const size_t partBytes = (size_t)nChunks * nPairs * HB * HB * sizeof(double);
     if (!ctx->d_W) MBAR_CUDA(cudaMalloc((void**)&ctx->d_W, partBytes));
-    const size_t smem = 256 + (size_t)2 * 2 * HB * HSTRIDE * sizeof(double);
-    MBAR_CUDA(cudaFuncSetAttribute(hessian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = 512 + (size_t)HNS * 2 * HPANEL;
+    static bool attr = false;
+    if (!attr) {
+        MBAR_CUDA(cudaFuncSetAttribute(hessian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
     const PassLayout lay{K};
     hessian_kernel<<<dim3(nPairs, nChunks), 256, smem, ctx->stream>>>(
         ctx->d_u, ctx->d_L, ctx->d_c + 2 * K, ctx->d_rowmask, K, ctx->N, ctx->nTiles, nChunks, ctx->d_W);
