@@ -32,7 +32,17 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256, 1)
+// Converts row `row` of a 128 x 32 energy panel into weights in place (swizzled store).
+__device__ __forceinline__ void convert_row(double* P, int row, int lane, double ck, bool act, bool valid,
+                                            double L, const double* tab) {
+    const double v = P[row * TILE_N + lane];
+    __syncwarp();   // every lane has read the row before any lane overwrites a permuted slot of it
+    double wv = 0.0;
+    if (valid && act) wv = exp_fast(fmax(ck - v - L, -800.0), tab);
+    P[row * TILE_N + (lane ^ ((row & 7) << 2))] = wv;
+}
+
+__global__ void __launch_bounds__(512, 1)
 hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
                const double* __restrict__ c, const unsigned long long* __restrict__ rowmask, int K,
                int64_t N, int64_t nTiles, int nChunks, double* __restrict__ Gpart) {
@@ -41,7 +51,7 @@ hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(tab + 32);             // [HNS]
     uint64_t* bar_empty = bar_full + 4;                                     // [HNS]
     unsigned char* ring = smem_raw + 512;                                   // [HNS][2][HPANEL]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;             // 16 warps
 
     int bi = 0, rem = blockIdx.x;                 // pairs enumerated (0,0),(1,0),(1,1),(2,0),...
     while (rem > bi) { rem -= bi + 1; ++bi; }
@@ -50,13 +60,12 @@ hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
     const int chunk = blockIdx.y;
     const int64_t t0 = nTiles * chunk / nChunks, t1 = nTiles * (chunk + 1) / nChunks;
     const int rowsI = min(HB, K - bi * HB), rowsJ = min(HB, K - bj * HB);
-    const uint32_t stageBytes = diag ? HPANEL : 2 * HPANEL;
 
     if (threadIdx.x < 32) tab[threadIdx.x] = MBAR_EXP_TABLE[threadIdx.x];
     if (threadIdx.x == 0) {
         for (int i = 0; i < HNS; ++i) {
             mbar_init(smem_u32(&bar_full[i]), 1);
-            mbar_init(smem_u32(&bar_empty[i]), 8);
+            mbar_init(smem_u32(&bar_empty[i]), 16);
         }
         mbar_fence_init();
     }
@@ -75,23 +84,25 @@ hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
         bulk_g2s(dst, base + (int64_t)bi * HB * TILE_N, bytesI, fb);
         if (!diag) bulk_g2s(dst + HPANEL, base + (int64_t)bj * HB * TILE_N, bytesJ, fb);
     };
-    if (threadIdx.x == 0)
-        for (int i = 0; i < HNS - 1; ++i) issue(i);
+    if (threadIdx.x == 0) {
+        issue(0);
+        issue(1);
+    }
 
-    // phase-1 mapping: lane = sample, warp fills rows warp*16 .. +15 of each panel
-    // phase-2 mapping: warp tile 64 (i) x 32 (j): wm = warp / 4 (0..1), wn = warp % 4 (0..3)
+    // conversion (vector fp64 pipe): warp owns rows warp*8 .. +7 of each panel, lane = sample.
+    // MMA (tensor pipe): warp tile 32 (i) x 32 (j): wm = warp / 4, wn = warp % 4.
     const int wm = warp >> 2, wn = warp & 3;
-    double acc[8][4][2];
+    double acc[4][4][2];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    double cI[16], cJ[16];
+    double cI[8], cJ[8];
     uint32_t actI = 0, actJ = 0;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        const int ki = bi * HB + warp * 16 + r, kj = bj * HB + warp * 16 + r;
+    for (int r = 0; r < 8; ++r) {
+        const int ki = bi * HB + warp * 8 + r, kj = bj * HB + warp * 8 + r;
         const bool ai = ki < K && ((rowmask[ki >> 6] >> (ki & 63)) & 1ull);
         const bool aj = kj < K && ((rowmask[kj >> 6] >> (kj & 63)) & 1ull);
         cI[r] = ai ? c[ki] : 0.0;
@@ -99,75 +110,74 @@ hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
         actI |= (uint32_t)ai << r;
         actJ |= (uint32_t)aj << r;
     }
-    // swizzled column of (row, n): n ^ ((row & 7) << 2); rows handled by this thread in phase 1 are
-    // warp*16 + r, so (row & 7) = r & 7.
     const int fragCol = lane & 3, fragRow = lane >> 2;   // DMMA fragment coordinates of this lane
+    const int nIter = (int)(t1 - t0);
 
-    int it = 0;
-    double Lnext = (t0 < t1) ? Lp[t0 * TILE_N + lane] : 0.0;
-    for (int64_t tile = t0; tile < t1; ++tile, ++it) {
-        const int slot = it % HNS;
-        if (threadIdx.x == 0) issue(it + HNS - 1);
-        const double L = Lnext;
-        if (tile + 1 < t1) Lnext = Lp[(tile + 1) * TILE_N + lane];
-        const bool valid = tile * TILE_N + lane < N;
-        mbar_wait(smem_u32(&bar_full[slot]), (it / HNS) & 1);
-        double* Pi = reinterpret_cast<double*>(ring + (size_t)slot * 2 * HPANEL);
-        double* Pj = diag ? Pi : Pi + HB * TILE_N;
-
-        // ---- phase 1: energies -> weights in place (read the 16 rows first, then write swizzled)
-        {
-            double v[16];
+    // prologue: weights of the first tile
+    if (nIter > 0) {
+        const double L = Lp[t0 * TILE_N + lane];
+        const bool valid = t0 * TILE_N + lane < N;
+        mbar_wait(smem_u32(&bar_full[0]), 0);
+        double* Pi = reinterpret_cast<double*>(ring);
+        double* Pj = Pi + HB * TILE_N;
 #pragma unroll
-            for (int r = 0; r < 16; ++r) v[r] = Pi[(warp * 16 + r) * TILE_N + lane];
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                double wv = 0.0;
-                if (valid && ((actI >> r) & 1u)) wv = exp_fast(fmax(cI[r] - v[r] - L, -800.0), tab);
-                Pi[(warp * 16 + r) * TILE_N + (lane ^ ((r & 7) << 2))] = wv;
-            }
-            if (!diag) {
-#pragma unroll
-                for (int r = 0; r < 16; ++r) v[r] = Pj[(warp * 16 + r) * TILE_N + lane];
-                __syncwarp();
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    double wv = 0.0;
-                    if (valid && ((actJ >> r) & 1u)) wv = exp_fast(fmax(cJ[r] - v[r] - L, -800.0), tab);
-                    Pj[(warp * 16 + r) * TILE_N + (lane ^ ((r & 7) << 2))] = wv;
-                }
-            }
+        for (int r = 0; r < 8; ++r) {
+            convert_row(Pi, warp * 8 + r, lane, cI[r], (actI >> r) & 1u, valid, L, tab);
+            if (!diag) convert_row(Pj, warp * 8 + r, lane, cJ[r], (actJ >> r) & 1u, valid, L, tab);
         }
-        __syncthreads();
-        // ---- phase 2: Ghat block += Pi Pj^T on the DMMA pipe
-        const double* Ai = Pi + (wm * 64 + fragRow) * TILE_N;
+    }
+    __syncthreads();
+
+    for (int it = 0; it < nIter; ++it) {
+        const int slot = it % HNS;
+        const int64_t tile = t0 + it;
+        if (threadIdx.x == 0) issue(it + 2);          // slot (it+2)%3 was released at the end of it-1
+        // the NEXT tile's energies are converted while this tile is multiplied (separate pipes)
+        const bool haveNext = it + 1 < nIter;
+        const int nslot = (it + 1) % HNS;
+        double Ln = 0.0;
+        bool validN = false;
+        if (haveNext) {
+            Ln = Lp[(tile + 1) * TILE_N + lane];
+            validN = (tile + 1) * TILE_N + lane < N;
+            mbar_wait(smem_u32(&bar_full[nslot]), ((it + 1) / HNS) & 1);
+        }
+        double* Ni = reinterpret_cast<double*>(ring + (size_t)nslot * 2 * HPANEL);
+        double* Nj = Ni + HB * TILE_N;
+        const double* Pi = reinterpret_cast<const double*>(ring + (size_t)slot * 2 * HPANEL);
+        const double* Pj = diag ? Pi : Pi + HB * TILE_N;
+        const double* Ai = Pi + (wm * 32 + fragRow) * TILE_N;
         const double* Bj = Pj + (wn * 32 + fragRow) * TILE_N;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
+            if (haveNext) {
+                convert_row(Ni, warp * 8 + ks, lane, cI[ks], (actI >> ks) & 1u, validN, Ln, tab);
+                if (!diag) convert_row(Nj, warp * 8 + ks, lane, cJ[ks], (actJ >> ks) & 1u, validN, Ln, tab);
+            }
             const int col = ((ks ^ fragRow) << 2) + fragCol;      // (4 ks + fragCol) ^ (fragRow << 2)
-            double a[8], b[4];
+            double a[4], b[4];
 #pragma unroll
-            for (int mt = 0; mt < 8; ++mt) a[mt] = Ai[mt * 8 * TILE_N + col];
+            for (int mt = 0; mt < 4; ++mt) a[mt] = Ai[mt * 8 * TILE_N + col];
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) b[nt] = Bj[nt * 8 * TILE_N + col];
 #pragma unroll
-            for (int mt = 0; mt < 8; ++mt)
+            for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
         }
-        fence_proxy_async_smem();   // the slot was written in place; the next writer is the TMA engine
+        fence_proxy_async_smem();   // slot `slot` was written in place; its next writer is the TMA engine
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar_empty[slot]));
+        __syncthreads();            // next tile's weights are complete for every warp
     }
     // write this CTA's 128 x 128 partial block: Gpart[chunk][pair][128][128]
     const int nPairs = gridDim.x;
     double* out = Gpart + ((size_t)chunk * nPairs + blockIdx.x) * HB * HB;
 #pragma unroll
-    for (int mt = 0; mt < 8; ++mt)
+    for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-            const int row = wm * 64 + mt * 8 + (lane >> 2);
+            const int row = wm * 32 + mt * 8 + (lane >> 2);
             const int col = wn * 32 + nt * 8 + (lane & 3) * 2;
             out[row * HB + col] = acc[mt][nt][0];
             out[row * HB + col + 1] = acc[mt][nt][1];
@@ -215,7 +225,7 @@ int launch_hessian(mbar_b200_ctx* ctx, const double* h_f) {
         attr = true;
     }
     const PassLayout lay{K};
-    hessian_kernel<<<dim3(nPairs, nChunks), 256, smem, ctx->stream>>>(
+    hessian_kernel<<<dim3(nPairs, nChunks), 512, smem, ctx->stream>>>(
         ctx->d_u, ctx->d_L, ctx->d_c + 2 * K, ctx->d_rowmask, K, ctx->N, ctx->nTiles, nChunks, ctx->d_W);
     MBAR_CUDA(cudaGetLastError());
     hessian_reduce_kernel<<<dim3(nPairs, 16), 256, 0, ctx->stream>>>(ctx->d_W, K, nPairs, nChunks,
