@@ -120,7 +120,7 @@ struct FusedParams {
     double* Lout;                          // [nTiles*32] shifted-frame L'_n, or NULL
     int64_t N, nTiles, nStages;
     double mid;
-    int K, Wk, Wn, Rw, TPW, NS, CW, batch, debugSkip;
+    int K, Wk, Wn, Rw, TPW, NS, CW, batch, debugSkip, mode;
     uint32_t tileBytes, stageBytes;
 };
 

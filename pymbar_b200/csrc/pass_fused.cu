@@ -49,23 +49,42 @@ __device__ __forceinline__ double lds_f64(const double* p) {
 // are issued right after the rounding step (5 polynomial stages ahead of their use) and the
 // energies of the NEXT batch are fetched before this batch's polynomial (volatile loads keep their
 // program position; two consumer warps per scheduler cannot hide ~30-cycle LDS otherwise).
-template <int R, int B, int R0, bool PREFETCH>
-__device__ __forceinline__ void exp_batch(const double (&cu)[B], const double (&uu)[B], int tabHi, int tabLo,
+// How the 2^(j/32) table is gathered and how the state constant enters:
+//   MODE bit 0: 0 = table entry `lane` in two registers, gathered with two index shuffles;
+//               1 = lane-replicated table in shared memory (tab[j][lane], 8 KB): one conflict-free
+//                   LDS.64 whose address is (n << 8 & 0x1f00) | laneBase — cheaper to issue than two SHFL;
+//   MODE bit 1: 0 = e = exp(c_k - u'), D += e                       (12 fp64 ops per entry)
+//               1 = e0 = exp(-u'), D += E_k * e0 with E_k = exp(c_k) (11 fp64 ops; needs spread(c) <= 600)
+struct TabRef {
+    int hi, lo;          // shuffle mode
+    uint32_t laneBase;   // LDS mode: shared address of tab[0][lane]
+};
+
+template <int R, int B, int R0, bool PREFETCH, int MODE>
+__device__ __forceinline__ void exp_batch(const double (&cu)[B], const double (&uu)[B], const TabRef tr,
                                           double (&e)[R], double& Dp, const double* nextC,
                                           const double* nextU, double (&cn)[B], double (&un)[B]) {
+    constexpr bool LDSTAB = MODE & 1, ETRICK = MODE & 2;
     double t[B], r[B], pl[B], T[B];
 #pragma unroll
     for (int i = 0; i < B; ++i) {
-        r[i] = cu[i] - uu[i];
-        t[i] = fma(r[i], MBAR_EXP_SCALE, EXP_MAGIC);
+        if (ETRICK) {
+            r[i] = uu[i];                                        // r holds +u' here (argument is -u')
+            t[i] = fma(uu[i], -MBAR_EXP_SCALE, EXP_MAGIC);
+        } else {
+            r[i] = cu[i] - uu[i];
+            t[i] = fma(r[i], MBAR_EXP_SCALE, EXP_MAGIC);
+        }
     }
-    // table lookup 2^(j/32), j = n & 31: every lane keeps entry `lane` in two 32-bit registers and
-    // the gather is a pair of index shuffles (the source lane is taken modulo 32 by the hardware):
-    // no address arithmetic, no shared-memory bank conflicts.
 #pragma unroll
     for (int i = 0; i < B; ++i) {
         const int n = __double2loint(t[i]);
-        T[i] = __hiloint2double(__shfl_sync(0xffffffffu, tabHi, n), __shfl_sync(0xffffffffu, tabLo, n));
+        if (LDSTAB) {
+            const uint32_t addr = (((uint32_t)n << 8) & 0x1f00u) | tr.laneBase;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(T[i]) : "r"(addr));
+        } else {
+            T[i] = __hiloint2double(__shfl_sync(0xffffffffu, tr.hi, n), __shfl_sync(0xffffffffu, tr.lo, n));
+        }
     }
     if (PREFETCH) {
 #pragma unroll
@@ -78,35 +97,52 @@ __device__ __forceinline__ void exp_batch(const double (&cu)[B], const double (&
             cn[i + 1] = c2.y;
         }
     }
+    if (ETRICK) {
+        // rp = u' + n*ln2/32 = -(reduced argument); odd coefficients carry the sign
 #pragma unroll
-    for (int i = 0; i < B; ++i) r[i] = fma(t[i] - EXP_MAGIC, -MBAR_EXP_LN2N, r[i]);
+        for (int i = 0; i < B; ++i) r[i] = fma(t[i] - EXP_MAGIC, MBAR_EXP_LN2N, r[i]);
 #pragma unroll
-    for (int i = 0; i < B; ++i) pl[i] = fma(MBAR_EXP_C5, r[i], MBAR_EXP_C4);
+        for (int i = 0; i < B; ++i) pl[i] = fma(-MBAR_EXP_C5, r[i], MBAR_EXP_C4);
 #pragma unroll
-    for (int i = 0; i < B; ++i) pl[i] = fma(pl[i], r[i], MBAR_EXP_C3);
+        for (int i = 0; i < B; ++i) pl[i] = fma(pl[i], r[i], -MBAR_EXP_C3);
 #pragma unroll
-    for (int i = 0; i < B; ++i) pl[i] = fma(pl[i], r[i], MBAR_EXP_C2);
+        for (int i = 0; i < B; ++i) pl[i] = fma(pl[i], r[i], MBAR_EXP_C2);
 #pragma unroll
-    for (int i = 0; i < B; ++i) pl[i] = fma(pl[i], r[i], MBAR_EXP_C1);
+        for (int i = 0; i < B; ++i) pl[i] = fma(pl[i], r[i], -MBAR_EXP_C1);
+    } else {
+#pragma unroll
+        for (int i = 0; i < B; ++i) r[i] = fma(t[i] - EXP_MAGIC, -MBAR_EXP_LN2N, r[i]);
+#pragma unroll
+        for (int i = 0; i < B; ++i) pl[i] = fma(MBAR_EXP_C5, r[i], MBAR_EXP_C4);
+#pragma unroll
+        for (int i = 0; i < B; ++i) pl[i] = fma(pl[i], r[i], MBAR_EXP_C3);
+#pragma unroll
+        for (int i = 0; i < B; ++i) pl[i] = fma(pl[i], r[i], MBAR_EXP_C2);
+#pragma unroll
+        for (int i = 0; i < B; ++i) pl[i] = fma(pl[i], r[i], MBAR_EXP_C1);
+    }
 #pragma unroll
     for (int i = 0; i < B; ++i) pl[i] = pl[i] * r[i];
 #pragma unroll
     for (int i = 0; i < B; ++i) {
         e[R0 + i] = scale2(fma(T[i], pl[i], T[i]), __double2loint(t[i]) >> 5);
-        Dp += e[R0 + i];
+        if (ETRICK)
+            Dp = fma(cu[i], e[R0 + i], Dp);
+        else
+            Dp += e[R0 + i];
     }
 }
 
 // All R rows of a thread in batches of B with two alternating input register sets (no copies).
-template <int R, int B, int R0>
+template <int R, int B, int R0, int MODE>
 __device__ __forceinline__ void exp_rows(double (&cA)[B], double (&uA)[B], double (&cB)[B], double (&uB)[B],
-                                         int tabHi, int tabLo, double (&e)[R], double& Dp,
+                                         const TabRef tr, double (&e)[R], double& Dp,
                                          const double* cbase, const double* ubase) {
     if constexpr (R0 + B < R) {
-        exp_batch<R, B, R0, true>(cA, uA, tabHi, tabLo, e, Dp, cbase + R0 + B, ubase + (R0 + B) * TILE_N, cB, uB);
-        exp_rows<R, B, R0 + B>(cB, uB, cA, uA, tabHi, tabLo, e, Dp, cbase, ubase);
+        exp_batch<R, B, R0, true, MODE>(cA, uA, tr, e, Dp, cbase + R0 + B, ubase + (R0 + B) * TILE_N, cB, uB);
+        exp_rows<R, B, R0 + B, MODE>(cB, uB, cA, uA, tr, e, Dp, cbase, ubase);
     } else {
-        exp_batch<R, B, R0, false>(cA, uA, tabHi, tabLo, e, Dp, nullptr, nullptr, cB, uB);
+        exp_batch<R, B, R0, false, MODE>(cA, uA, tr, e, Dp, nullptr, nullptr, cB, uB);
     }
 }
 
@@ -123,7 +159,7 @@ __device__ __forceinline__ void logprod_renorm(double& mprod, int& esum) {
     mprod = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(mprod));
 }
 
-template <int R, bool FULL, int CW, int BATCH>
+template <int R, bool FULL, int CW, int BATCH, int MODE>
 __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int K = p.K;
@@ -140,7 +176,13 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 32) tab[threadIdx.x] = MBAR_EXP_TABLE[threadIdx.x];
-    for (int k = threadIdx.x; k < K; k += blockDim.x) c_s[k] = p.c[k];
+    // state constants: c_k, or E_k = exp(c_k) when the constant is applied multiplicatively
+    for (int k = threadIdx.x; k < K; k += blockDim.x) c_s[k] = (FULL && (MODE & 2)) ? exp(p.c[k]) : p.c[k];
+    // lane-replicated exp table, 8 KB aligned so that its address bits never overlap the index bits
+    const uint32_t tabRep = (smem_u32(stages + (size_t)p.NS * p.stageBytes) + 8191u) & ~8191u;
+    if (FULL && (MODE & 1))
+        for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x)
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(tabRep + i * 8), "d"(MBAR_EXP_TABLE[i >> 5]));
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.NS; ++i) {
             mbar_init(smem_u32(&bar_full[i]), 1);
@@ -191,8 +233,10 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
         int it = 0;
         double mprod = 1.0;   // running product of the mantissas of D_n (see logprod_push)
         int esum = 0, npush = 0;
-        const int tabHi = __double2hiint(MBAR_EXP_TABLE[lane]);
-        const int tabLo = __double2loint(MBAR_EXP_TABLE[lane]);
+        TabRef tr;
+        tr.hi = __double2hiint(MBAR_EXP_TABLE[lane]);
+        tr.lo = __double2loint(MBAR_EXP_TABLE[lane]);
+        tr.laneBase = tabRep + lane * 8;
         for (int64_t s = blockIdx.x; s < p.nStages; s += gridDim.x, ++it) {
             const int slot = it % p.NS;
             // keep NS-1 stages in flight: stage it+NS-1 goes into the slot consumed at iteration it-1,
@@ -217,7 +261,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                         uA[i] = lds_f64(tp + i * TILE_N);
                         cA[i] = lds_f64(c_s + k0 + i);
                     }
-                    exp_rows<R, B, 0>(cA, uA, cB, uB, tabHi, tabLo, e, Dp, c_s + k0, tp);
+                    exp_rows<R, B, 0, MODE>(cA, uA, cB, uB, tr, e, Dp, c_s + k0, tp);
                 } else {
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
@@ -301,6 +345,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
         const bool act = (p.rowmask[k >> 6] >> (k & 63)) & 1ull;
         double t = 0.0;
         for (unsigned b = 0; b < gridDim.x; ++b) t += p.partial[(size_t)b * (K + 2) + k];
+        if (FULL && (MODE & 2)) t *= exp(p.c[k]);     // S_k = E_k * sum_n e0_kn / D_n / N_k
         p.out[lay.S() + k] = act ? t / p.Nk[k] : 0.0;
         p.out[lay.logS() + k] = 0.0;
     }
@@ -339,18 +384,28 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams
     if (K > 256) return MBAR_B200_OK;
     FusedParams p{};
     p.K = K;
-    // variant: consumer warps CW and rows per thread.  MBAR_B200_FUSED_VARIANT = "cw,batch" overrides.
-    int cw = 8, batch = 8;
-    if (const char* v = std::getenv("MBAR_B200_FUSED_VARIANT")) std::sscanf(v, "%d,%d", &cw, &batch);
-    if (cw != 16) cw = 8;
-    if (batch != 4 && batch != 16) batch = 8;
-    const int rmax = (cw == 16) ? 16 : 32;
+    // kernel mode (see TabRef): bit 0 = LDS-replicated exp table, bit 1 = multiplicative state constant.
+    // MBAR_B200_FUSED_MODE overrides the default for experiments.
+    int mode = 3;
+    if (const char* v = std::getenv("MBAR_B200_FUSED_MODE")) mode = std::atoi(v) & 3;
+    {
+        double lo = INFINITY, hi = -INFINITY;
+        for (int k : ctx->active) {
+            const double c = h_f[k] + ctx->h_logNk[k];
+            lo = std::fmin(lo, c);
+            hi = std::fmax(hi, c);
+        }
+        if (hi - lo > 600.0) mode &= 1;   // exp(c_k) * exp(-u') needs the spread inside the exponent range
+    }
+    const int cw = 8;
+    const int rmax = 32;
     int wk = 1;
     while (wk * rmax < K) wk *= 2;
     p.Wk = wk;
     p.CW = cw;
+    p.batch = 8;
+    p.mode = mode;
     p.debugSkip = std::getenv("MBAR_B200_FUSED_SKIP") ? 1 : 0;
-    p.batch = batch;
     p.Wn = cw / p.Wk;
     p.Rw = (K + p.Wk - 1) / p.Wk;
     p.tileBytes = (uint32_t)K * TILE_N * 8;
@@ -358,7 +413,7 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams
     p.TPW = tpw < 1 ? 1 : (tpw > 8 ? 8 : tpw);
     p.stageBytes = (uint32_t)p.Wn * p.TPW * p.tileBytes;
     const size_t header = fused_smem_header(K);
-    int ns = (int)((225 * 1024 - header) / p.stageBytes);
+    int ns = (int)((225 * 1024 - header - ((mode & 1) ? 16384 : 0)) / p.stageBytes);
     p.NS = ns > 8 ? 8 : ns;
     if (p.NS < 2) return MBAR_B200_OK;
     const int tilesPerStage = p.Wn * p.TPW;
@@ -388,36 +443,22 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams
 
 // Launch with whatever c currently sits in ctx->d_c (device-resident iteration).
 int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
-    const size_t smem = fused_smem_header(p.K) + (size_t)p.NS * p.stageBytes;
+    const size_t smem = fused_smem_header(p.K) + (size_t)p.NS * p.stageBytes + ((p.mode & 1) ? 16384 : 0);
     int64_t grid = p.nStages < ctx->smCount ? p.nStages : ctx->smCount;
     const int Rt = p.Rw <= 8 ? 8 : p.Rw <= 16 ? 16 : 32;
     const bool full = (p.Rw == Rt) && (p.K == p.Wk * p.Rw) && ((int)ctx->active.size() == p.K);
     void (*kern)(const FusedParams) = nullptr;
     int which = 0;
-#define PICK(R_, F_, CW_, B_, ID_)                                                    \
-    if (Rt == R_ && full == F_ && p.CW == CW_ && p.batch == B_) {                     \
-        kern = pass_fused_kernel<R_, F_, CW_, B_>;                                    \
-        which = ID_;                                                                  \
+#define PICK(R_, ID_)                                                                          \
+    if (Rt == R_) {                                                                            \
+        if (!full) { kern = pass_fused_kernel<R_, false, 8, 8, 0>; which = ID_; }              \
+        else if (p.mode == 0) { kern = pass_fused_kernel<R_, true, 8, 8, 0>; which = ID_ + 1; } \
+        else if (p.mode == 1) { kern = pass_fused_kernel<R_, true, 8, 8, 1>; which = ID_ + 2; } \
+        else if (p.mode == 2) { kern = pass_fused_kernel<R_, true, 8, 8, 2>; which = ID_ + 3; } \
+        else { kern = pass_fused_kernel<R_, true, 8, 8, 3>; which = ID_ + 4; }                  \
     }
-    PICK(8, true, 8, 8, 0) PICK(16, true, 8, 8, 1) PICK(32, true, 8, 8, 2)
-    PICK(8, false, 8, 8, 3) PICK(16, false, 8, 8, 4) PICK(32, false, 8, 8, 5)
-    PICK(32, true, 8, 16, 6) PICK(32, true, 8, 4, 7)
-    PICK(8, true, 16, 8, 8) PICK(16, true, 16, 8, 9) PICK(16, true, 16, 4, 10) PICK(16, true, 16, 16, 11)
-    PICK(8, false, 16, 8, 12) PICK(16, false, 16, 8, 13)
+    PICK(8, 0) PICK(16, 5) PICK(32, 10)
 #undef PICK
-    if (!kern) {  // unsupported experimental combination: fall back to the default variant family
-        const int b = 8;
-        (void)b;
-        if (p.CW == 16) {
-            kern = full ? (Rt == 8 ? pass_fused_kernel<8, true, 16, 8> : pass_fused_kernel<16, true, 16, 8>)
-                        : (Rt == 8 ? pass_fused_kernel<8, false, 16, 8> : pass_fused_kernel<16, false, 16, 8>);
-            which = full ? (Rt == 8 ? 8 : 9) : (Rt == 8 ? 12 : 13);
-        } else {
-            kern = full ? (Rt == 8 ? pass_fused_kernel<8, true, 8, 8> : Rt == 16 ? pass_fused_kernel<16, true, 8, 8> : pass_fused_kernel<32, true, 8, 8>)
-                        : (Rt == 8 ? pass_fused_kernel<8, false, 8, 8> : Rt == 16 ? pass_fused_kernel<16, false, 8, 8> : pass_fused_kernel<32, false, 8, 8>);
-            which = (Rt == 8 ? 0 : Rt == 16 ? 1 : 2) + (full ? 0 : 3);
-        }
-    }
     static size_t attrSet[16] = {0};
     if (attrSet[which] < smem) {
         MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

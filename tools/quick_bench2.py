@@ -14,5 +14,5 @@ for K, N in cfgs:
     p.gradient(f); ms = []
     for _ in range(10):
         p.gradient(f); ms.append(p.last_pass_ms())
-    print(f"[{os.environ.get('MBAR_B200_FUSED_VARIANT','default')}] K={K} N={N:.0e} fused min {min(ms):.3f} med {np.median(ms):.3f} ms -> {8*K*N/min(ms)/1e6:.0f} GB/s", flush=True)
+    print(f"[mode {os.environ.get("MBAR_B200_FUSED_MODE","default")}] K={K} N={N:.0e} fused min {min(ms):.3f} med {np.median(ms):.3f} ms -> {8*K*N/min(ms)/1e6:.0f} GB/s", flush=True)
     p.close()
