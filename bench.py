@@ -235,6 +235,11 @@ def run_ours(args):
         uid = [DeviceProblem.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         prob.comm_init(world, rank, uid[0])
+        if not os.environ.get("MBAR_B200_NO_PEER"):
+            # in-kernel exchange of the partial sums over peer memory (one kernel per iteration)
+            handles = [None] * world
+            dist.all_gather_object(handles, prob.peer_export())
+            prob.peer_attach(world, rank, handles)
 
     def barrier():
         if distributed:
@@ -328,7 +333,10 @@ def run_ours(args):
             "config": {"workload": "MBAR self-consistent iteration (Eq. C3), synthetic harmonic u_kn, "
                                    "K=256, N=1e7 per GPU, fp64, device-resident, samples sharded over GPUs",
                        "K": K, "N_per_gpu": N_local, "N_total": N_total, "seed": args.seed,
-                       "parallelism": f"sample-sharded x{world}, 1 all-reduce of {K + 2} doubles per iteration",
+                       "parallelism": f"sample-sharded x{world}; per iteration the {K + 2} partial sums are exchanged "
+                                      + ("inside the pass kernel over NVLink peer memory (rank-ordered sum)"
+                                         if (distributed and not os.environ.get("MBAR_B200_NO_PEER")) else
+                                         "by one NCCL all-reduce" if distributed else "n/a (1 GPU)"),
                        "l2": "inputs (20.48 GB per GPU) far larger than the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the launching stream around the K-step loop, max over ranks",
                        "wall_s_rank0": wall},

@@ -164,6 +164,15 @@ int mbar_b200_comm_unique_id(void* id_out /* [128] */);
 int mbar_b200_comm_init(mbar_b200_ctx* ctx, int32_t nranks, int32_t rank, const void* unique_id);
 int mbar_b200_comm_destroy(mbar_b200_ctx* ctx);
 
+/* Peer-memory exchange for the device-resident iteration: every rank exports a 64-byte cudaIpc handle
+ * of its inbox, the caller distributes them (any transport), every rank attaches all of them.  After
+ * that mbar_b200_sci_iterate runs ONE kernel per iteration: the pass kernel's last CTA stores its
+ * K+2 partial sums into every peer's inbox over NVLink, waits for the peers' flags, sums in rank order
+ * and applies the K-vector update — no NCCL call and no second launch on the iteration's critical path. */
+#define MBAR_B200_IPC_HANDLE_BYTES 64
+int mbar_b200_peer_export(mbar_b200_ctx* ctx, void* handle_out /* [64] */);
+int mbar_b200_peer_attach(mbar_b200_ctx* ctx, int32_t nranks, int32_t rank, const void* handles /* [nranks][64] */);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

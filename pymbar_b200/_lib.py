@@ -71,6 +71,8 @@ SIGNATURES = {
     "mbar_b200_comm_unique_id": (C.c_int, [C.c_void_p]),
     "mbar_b200_comm_init": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.c_void_p]),
     "mbar_b200_comm_destroy": (C.c_int, [_ctx]),
+    "mbar_b200_peer_export": (C.c_int, [_ctx, C.c_void_p]),
+    "mbar_b200_peer_attach": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.c_void_p]),
 }
 
 _lib = None

@@ -573,14 +573,27 @@ int mbar_b200_sci_iterate(mbar_b200_ctx* c, double* f, int32_t iters) {
     MBAR_CUDA(cudaEventCreate(&l0));
     MBAR_CUDA(cudaEventCreate(&l1));
     MBAR_CUDA(cudaEventRecord(l0, c->stream));
+    // One kernel per iteration when the exchange can live inside the pass kernel (single GPU, or peers
+    // attached through mbar_b200_peer_attach); otherwise pass -> ncclAllReduce -> epilogue kernel.
+    const bool inKernel = (c->nranks == 1 || c->peerReady) && !std::getenv("MBAR_B200_NO_FUSED_EPILOGUE");
+    if (inKernel) {
+        p.epi = 1;
+        p.f = c->d_f;
+        p.cnext = c->d_c;
+        p.first = c->firstActive;
+        if (c->peerReady) p.peer = c->peer;
+    }
     for (int it = 0; it < iters; ++it) {
         if (perLaunch) MBAR_CUDA(cudaEventRecord(ev[2 * it], c->stream));
+        p.seq = ++c->peerSeq;
         MBAR_TRY(fused_enqueue(c, p));
         if (perLaunch) MBAR_CUDA(cudaEventRecord(ev[2 * it + 1], c->stream));
-        MBAR_TRY(comm_allreduce(c, c->d_out, K + 2, 0));
-        sci_epilogue_kernel<<<1, threads, 0, c->stream>>>(c->d_out, c->d_f, c->d_c, c->d_Nk, K, c->firstActive,
-                                                         p.mid, c->d_scratch);
-        c->launches++;
+        if (!inKernel) {
+            MBAR_TRY(comm_allreduce(c, c->d_out, K + 2, 0));
+            sci_epilogue_kernel<<<1, threads, 0, c->stream>>>(c->d_out, c->d_f, c->d_c, c->d_Nk, K,
+                                                             c->firstActive, p.mid, c->d_scratch);
+            c->launches++;
+        }
     }
     MBAR_CUDA(cudaEventRecord(l1, c->stream));
     MBAR_CUDA(cudaEventSynchronize(l1));
@@ -609,6 +622,8 @@ int mbar_b200_sci_iterate(mbar_b200_ctx* c, double* f, int32_t iters) {
     c->d2hBytes += K * 8 + lay.size(false) * 8;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->evA, c->evB) == cudaSuccess) c->lastPassMs = ms;
+    MBAR_REQUIRE(!(iters > 0 && c->h_out[lay.flag()] >= 1.0e6), MBAR_B200_ERR_COMM,
+                 "peer exchange timed out inside the pass kernel (a rank did not arrive)");
     if (iters > 0 && c->h_out[lay.flag()] != 0.0) c->h_f[4 * K + c->firstActive] = NAN;  // force the robust redo
     bool finite = true;
     for (int k : c->active) finite = finite && std::isfinite(c->h_f[4 * K + k]);
@@ -674,6 +689,51 @@ int mbar_b200_comm_init(mbar_b200_ctx* c, int32_t nranks, int32_t rank, const vo
     c->comm = comm;
     c->nranks = nranks;
     c->rank = rank;
+    return MBAR_B200_OK;
+}
+
+static size_t inbox_doubles(int K) { return (size_t)2 * 8 * (K + 2); }
+
+int mbar_b200_peer_export(mbar_b200_ctx* c, void* handle_out) {
+    MBAR_REQUIRE(c && handle_out, MBAR_B200_ERR_INVALID, "NULL argument");
+    MBAR_CUDA(cudaSetDevice(c->device));
+    if (!c->d_inbox) {
+        const size_t bytes = inbox_doubles(c->K) * sizeof(double) + 2 * 8 * sizeof(unsigned long long);
+        MBAR_CUDA(cudaMalloc((void**)&c->d_inbox, bytes));
+        MBAR_CUDA(cudaMemset(c->d_inbox, 0, bytes));
+    }
+    cudaIpcMemHandle_t h;
+    MBAR_CUDA(cudaIpcGetMemHandle(&h, c->d_inbox));
+    static_assert(sizeof(h) == MBAR_B200_IPC_HANDLE_BYTES, "ipc handle size");
+    std::memcpy(handle_out, &h, sizeof(h));
+    return MBAR_B200_OK;
+}
+
+int mbar_b200_peer_attach(mbar_b200_ctx* c, int32_t nranks, int32_t rank, const void* handles) {
+    MBAR_REQUIRE(c && handles, MBAR_B200_ERR_INVALID, "NULL argument");
+    MBAR_REQUIRE(nranks >= 1 && nranks <= 8 && rank >= 0 && rank < nranks, MBAR_B200_ERR_INVALID,
+                 "rank %d of %d (at most 8 peers)", rank, nranks);
+    MBAR_REQUIRE(c->d_inbox, MBAR_B200_ERR_NOT_READY, "call mbar_b200_peer_export first");
+    MBAR_CUDA(cudaSetDevice(c->device));
+    c->peer = PeerCfg{};
+    c->peer.nranks = nranks;
+    c->peer.rank = rank;
+    for (int q = 0; q < nranks; ++q) {
+        void* ptr = c->d_inbox;
+        if (q != rank) {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, static_cast<const char*>(handles) + (size_t)q * sizeof(h), sizeof(h));
+            MBAR_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            c->peerMapped.push_back(ptr);
+        }
+        c->peer.inbox[q] = static_cast<double*>(ptr);
+        c->peer.flags[q] = reinterpret_cast<unsigned long long*>(static_cast<double*>(ptr) + inbox_doubles(c->K));
+    }
+    c->peerReady = nranks > 1;
+    if (c->nranks == 1) {           // peers without an NCCL communicator: still a sharded problem
+        c->nranks = nranks;
+        c->rank = rank;
+    }
     return MBAR_B200_OK;
 }
 

@@ -365,6 +365,8 @@ int mbar_b200_destroy(mbar_b200_ctx* c) {
     if (!c) return MBAR_B200_OK;
     cudaSetDevice(c->device);
     if (c->comm) mbar_b200_comm_destroy(c);
+    for (void* pm : c->peerMapped) cudaIpcCloseMemHandle(pm);
+    cudaFree(c->d_inbox);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_u); cudaFree(c->d_xshift); cudaFree(c->d_c); cudaFree(c->d_Nk);
     cudaFree(c->d_rowmask); cudaFree(c->d_zeromask); cudaFree(c->d_partial); cudaFree(c->d_out); cudaFree(c->d_L);

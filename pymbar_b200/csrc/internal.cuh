@@ -53,6 +53,13 @@ struct PassLayout {
     __host__ __device__ int size(bool withG) const { return 2 * K + 2 + (withG ? K * K : 0); }
 };
 
+// Peer-memory exchange of the per-pass partial sums (fused into the pass kernel's last CTA).
+struct PeerCfg {
+    int nranks = 1, rank = 0;
+    double* inbox[8] = {nullptr};               // inbox[q]: rank q's [2][nranks][K+2] buffer, mapped here
+    unsigned long long* flags[8] = {nullptr};   // flags[q]: rank q's [2][nranks] sequence numbers
+};
+
 }  // namespace mbar
 
 struct mbar_b200_ctx {
@@ -95,6 +102,13 @@ struct mbar_b200_ctx {
     double* stage_dev[2] = {nullptr, nullptr};
     int64_t stageCols = 0;
 
+    // peer-memory exchange (cudaIpc): this rank's inbox + flags and the peers' mappings
+    double* d_inbox = nullptr;
+    mbar::PeerCfg peer;
+    bool peerReady = false;
+    unsigned long long peerSeq = 0;
+    std::vector<void*> peerMapped;
+
     // communicator (NCCL, dlopen'd)
     void* comm = nullptr;
     int nranks = 1, rank = 0;
@@ -118,6 +132,11 @@ struct FusedParams {
     double* out;
     unsigned int* ticket;
     double* Lout;                          // [nTiles*32] shifted-frame L'_n, or NULL
+    double* f;                             // [K] device f_k (epilogue) or NULL
+    double* cnext;                         // [K] where the epilogue writes c for the next launch
+    PeerCfg peer;
+    unsigned long long seq;                // exchange sequence number (>= 1)
+    int epi, first;
     int64_t N, nTiles, nStages;
     double mid;
     int K, Wk, Wn, Rw, TPW, NS, CW, batch, debugSkip, mode;

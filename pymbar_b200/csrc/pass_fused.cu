@@ -204,11 +204,11 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
     // Producer duty rides on thread 0 (a dedicated producer warp would put a third warp on one
     // scheduler and cut the register budget of EVERY thread from 255 to 168).  `issue(it)` streams the
     // it-th stage of this CTA into ring slot it % NS.
-    auto issue = [&](int it2) {
+    // (slot, wrap) are carried incrementally by the callers: no integer division in the loop
+    auto issue = [&](int it2, int slot2, int wrap2) {
         const int64_t s2 = (int64_t)blockIdx.x + (int64_t)it2 * gridDim.x;
         if (s2 >= p.nStages) return;
-        const int slot2 = it2 % p.NS;
-        if (it2 >= p.NS) mbar_wait(smem_u32(&bar_empty[slot2]), ((it2 / p.NS) - 1) & 1);
+        if (wrap2 > 0) mbar_wait(smem_u32(&bar_empty[slot2]), (wrap2 - 1) & 1);
         const int64_t tile0 = s2 * tilesPerStage;
         const int64_t ntl = min((int64_t)tilesPerStage, p.nTiles - tile0);
         const uint32_t bytes = (uint32_t)ntl * p.tileBytes;
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
             bulk_g2s(dst + off, src + off, min(FUSED_COPY_CHUNK, bytes - off), fb);
     };
     if (threadIdx.x == 0)
-        for (int i = 0; i < p.NS - 1; ++i) issue(i);
+        for (int i = 0; i < p.NS - 1; ++i) issue(i, i, 0);
     {
         // ------------------------------ consumers -----------------------------
         uint32_t actbits = 0;
@@ -237,12 +237,14 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
         tr.hi = __double2hiint(MBAR_EXP_TABLE[lane]);
         tr.lo = __double2loint(MBAR_EXP_TABLE[lane]);
         tr.laneBase = tabRep + lane * 8;
+        int slot = 0, wrap = 0;              // it = wrap * NS + slot
+        int pslot = p.NS - 1, pwrap = 0;     // ring position of stage it + NS - 1
         for (int64_t s = blockIdx.x; s < p.nStages; s += gridDim.x, ++it) {
-            const int slot = it % p.NS;
             // keep NS-1 stages in flight: stage it+NS-1 goes into the slot consumed at iteration it-1,
             // which every warp released before it could pass that iteration's denominator barrier
-            if (threadIdx.x == 0) issue(it + p.NS - 1);
-            mbar_wait(smem_u32(&bar_full[slot]), (it / p.NS) & 1);
+            if (threadIdx.x == 0) issue(it + p.NS - 1, pslot, pwrap);
+            if (++pslot == p.NS) { pslot = 0; ++pwrap; }
+            mbar_wait(smem_u32(&bar_full[slot]), wrap & 1);
             const double* sb = reinterpret_cast<const double*>(stages + (size_t)slot * p.stageBytes);
             for (int j = 0; j < p.TPW; ++j) {
                 if (p.debugSkip) break;   // development probe: memory pipeline only
@@ -298,6 +300,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_empty[slot]));
+            if (++slot == p.NS) { slot = 0; ++wrap; }
         }
         // per-warp lane reduction of the R accumulators (once per kernel)
 #pragma unroll
@@ -341,22 +344,86 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
     if (!s_last) return;
     __threadfence();
     const PassLayout lay{K};
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        const bool act = (p.rowmask[k >> 6] >> (k & 63)) & 1ull;
+    // ---- last CTA: deterministic reduction over CTAs, optional exchange with the other GPUs, optional
+    // ---- self-consistent epilogue (f <- f - log S, gauge, c for the next launch): one kernel per iteration
+    double* tot = reinterpret_cast<double*>(stages);     // [K + 2] (the ring is idle now)
+    for (int k = threadIdx.x; k < K + 2; k += blockDim.x) {
         double t = 0.0;
         for (unsigned b = 0; b < gridDim.x; ++b) t += p.partial[(size_t)b * (K + 2) + k];
+        if (k == K) t += (double)p.N * p.mid;
+        tot[k] = t;
+    }
+    __syncthreads();
+    if (p.peer.nranks > 1) {
+        // One-shot all-gather of the K+2 partial sums through peer memory (NVLink stores into every
+        // rank's inbox, then a release flag), followed by a sum in RANK ORDER so that every GPU
+        // computes bit-identical totals.  Replaces ncclAllReduce + a separate epilogue launch.
+        const int par = (int)(p.seq & 1ull);
+        const int P = p.peer.nranks, me = p.peer.rank;
+        for (int q = 0; q < P; ++q) {
+            double* dst = p.peer.inbox[q] + ((size_t)par * P + me) * (K + 2);
+            for (int k = threadIdx.x; k < K + 2; k += blockDim.x) dst[k] = tot[k];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < P) {
+            unsigned long long* flag = p.peer.flags[threadIdx.x] + (size_t)par * P + me;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(p.seq) : "memory");
+        }
+        __shared__ int s_timeout;
+        if (threadIdx.x == 0) s_timeout = 0;
+        __syncthreads();
+        if (threadIdx.x < P) {
+            const unsigned long long* flag = p.peer.flags[me] + (size_t)par * P + threadIdx.x;
+            const long long t0 = clock64();
+            unsigned long long v;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+                if (v == p.seq) break;
+                if (clock64() - t0 > 4000000000ll) {   // ~2 s: a peer died; fail instead of hanging the GPU
+                    s_timeout = 1;
+                    break;
+                }
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+        const double* in = p.peer.inbox[me] + (size_t)par * P * (K + 2);
+        for (int k = threadIdx.x; k < K + 2; k += blockDim.x) {
+            double t = 0.0;
+            for (int q = 0; q < P; ++q) t += __ldcv(in + (size_t)q * (K + 2) + k);
+            tot[k] = t;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && s_timeout) tot[K + 1] += 1.0e6;   // flag > 0 -> host reports the failure
+        __syncthreads();
+    }
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const bool act = (p.rowmask[k >> 6] >> (k & 63)) & 1ull;
+        double t = tot[k];
         if (FULL && (MODE & 2)) t *= exp(p.c[k]);     // S_k = E_k * sum_n e0_kn / D_n / N_k
-        p.out[lay.S() + k] = act ? t / p.Nk[k] : 0.0;
+        t = act ? t / p.Nk[k] : 0.0;
+        p.out[lay.S() + k] = t;
         p.out[lay.logS() + k] = 0.0;
+        tot[k] = t;
     }
     if (threadIdx.x == 0) {
-        double t = 0.0, b = 0.0;
-        for (unsigned i = 0; i < gridDim.x; ++i) {
-            t += p.partial[(size_t)i * (K + 2) + K];
-            b += p.partial[(size_t)i * (K + 2) + K + 1];
+        p.out[lay.sumL()] = tot[K];
+        p.out[lay.flag()] = tot[K + 1];
+    }
+    if (p.epi) {
+        __syncthreads();
+        __shared__ double s_f0;
+        if (threadIdx.x == 0) s_f0 = p.f[p.first] - log(tot[p.first]);
+        __syncthreads();
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            if (p.Nk[k] > 0.0) {
+                // an underflowed S_k poisons the result so the host redoes the step in the log domain
+                const double fn = (tot[k] > 1e-280) ? p.f[k] - log(tot[k]) - s_f0 : NAN;
+                p.f[k] = fn;
+                p.cnext[k] = fn + log(p.Nk[k]) - p.mid;
+            }
         }
-        p.out[lay.sumL()] = t + (double)p.N * p.mid;
-        p.out[lay.flag()] = b;
     }
 }
 

@@ -154,6 +154,16 @@ class DeviceProblem:
         buf = C.create_string_buffer(bytes(unique_id), _lib.UNIQUE_ID_BYTES)
         check(self._lib.mbar_b200_comm_init(self._h, int(nranks), int(rank), buf))
 
+    def peer_export(self):
+        buf = C.create_string_buffer(64)
+        check(self._lib.mbar_b200_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_attach(self, nranks, rank, handles):
+        blob = b"".join(bytes(h) for h in handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        check(self._lib.mbar_b200_peer_attach(self._h, int(nranks), int(rank), buf))
+
     # ---- the pass and the reference primitives ----------------------------------------------------
     def _bad(self, f):
         """The reference propagates NaN through its primitives; the C ABI

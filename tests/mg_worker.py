@@ -44,12 +44,23 @@ def main():
         ref = np.zeros(len(N))
         ref[s] = z["adaptive_x"]
         errs["adaptive"] = np.max(np.abs(fk[s] - ref[s]))
-        f5 = p.sci_iterate(np.zeros(len(N)), 5)
+        f5 = p.sci_iterate(np.zeros(len(N)), 5)          # NCCL all-reduce + epilogue kernel
+        handles = [None] * world
+        dist.all_gather_object(handles, p.peer_export())
+        p.peer_attach(world, rank, handles)
+        f5p = p.sci_iterate(np.zeros(len(N)), 5)         # in-kernel exchange over peer memory
+        f5p = p.sci_iterate(f5p, 0)
+        errs_peer = np.max(np.abs(f5p[s] - f5[s]))
         fh = np.zeros(len(N))
         for _ in range(5):
             nxt = orc.self_consistent_update(u[s], N[s], fh[s])
             fh[s] = nxt - nxt[0]
         errs["sci_iterate"] = np.max(np.abs(f5[s] - fh[s]))
+        errs["sci_iterate_peer_vs_nccl"] = errs_peer
+        # every rank must hold bit-identical f after the in-kernel exchange (rank-ordered sum)
+        g = [None] * world
+        dist.all_gather_object(g, f5p.tobytes())
+        assert all(b == g[0] for b in g), "ranks disagree after the peer exchange"
         bad = {k: v for k, v in errs.items() if not v < 1e-8}
         worst = max(worst, max(errs.values()))
         assert not bad, (name, rank, bad)
