@@ -139,7 +139,7 @@ struct FusedParams {
     int epi, first;
     int64_t N, nTiles, nStages;
     double mid;
-    int K, Wk, Wn, Rw, TPW, NS, CW, batch, debugSkip, mode;
+    int K, Wk, Wn, Rw, TPW, NS, CW, batch, debugSkip, mode, CL, Kh;
     uint32_t tileBytes, stageBytes;
 };
 

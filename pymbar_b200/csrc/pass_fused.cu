@@ -159,10 +159,33 @@ __device__ __forceinline__ void logprod_renorm(double& mprod, int& esum) {
     mprod = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(mprod));
 }
 
-template <int R, bool FULL, int CW, int BATCH, int MODE>
+// ---- thread-block-cluster helpers (CL = 2: two CTAs on two SMs share one tile, half the states each)
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f64(double* localPtr, unsigned rank, double v) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(localPtr)), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// CL = 1: one CTA per tile group, K <= 256.  CL = 2 (256 < K <= 512): a cluster of two CTAs works on the
+// same tile; CTA `half` owns states [half*Kh, ...), pulls only those rows from HBM (no redundant
+// traffic) and the per-sample denominators are completed by exchanging the warps' partial sums
+// through distributed shared memory + one cluster barrier per tile.
+template <int R, bool FULL, int CW, int BATCH, int MODE, int CL>
 __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int K = p.K;
+    const int half = (CL == 2) ? (int)cluster_ctarank() : 0;
+    const int kbase = (CL == 2) ? half * p.Kh : 0;                       // first state of this CTA
+    const int Kl = (CL == 2) ? (half ? K - p.Kh : p.Kh) : K;            // states of this CTA
+    const unsigned nGroups = gridDim.x / CL, grp = blockIdx.x / CL;      // CTA (pair) index
     double* tab = reinterpret_cast<double*>(smem_raw);
     double* c_s = tab + 32;
     double* xD = c_s + K;                        // [2][CW warps][32]
@@ -177,7 +200,8 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 32) tab[threadIdx.x] = MBAR_EXP_TABLE[threadIdx.x];
     // state constants: c_k, or E_k = exp(c_k) when the constant is applied multiplicatively
-    for (int k = threadIdx.x; k < K; k += blockDim.x) c_s[k] = (FULL && (MODE & 2)) ? exp(p.c[k]) : p.c[k];
+    for (int k = threadIdx.x; k < Kl; k += blockDim.x)
+        c_s[k] = (FULL && (MODE & 2)) ? exp(p.c[kbase + k]) : p.c[kbase + k];
     // lane-replicated exp table, 8 KB aligned so that its address bits never overlap the index bits
     const uint32_t tabRep = (smem_u32(stages + (size_t)p.NS * p.stageBytes) + 8191u) & ~8191u;
     if (FULL && (MODE & 1))
@@ -206,18 +230,29 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
     // it-th stage of this CTA into ring slot it % NS.
     // (slot, wrap) are carried incrementally by the callers: no integer division in the loop
     auto issue = [&](int it2, int slot2, int wrap2) {
-        const int64_t s2 = (int64_t)blockIdx.x + (int64_t)it2 * gridDim.x;
+        const int64_t s2 = (int64_t)grp + (int64_t)it2 * nGroups;
         if (s2 >= p.nStages) return;
         if (wrap2 > 0) mbar_wait(smem_u32(&bar_empty[slot2]), (wrap2 - 1) & 1);
         const int64_t tile0 = s2 * tilesPerStage;
         const int64_t ntl = min((int64_t)tilesPerStage, p.nTiles - tile0);
-        const uint32_t bytes = (uint32_t)ntl * p.tileBytes;
         const uint32_t fb = smem_u32(&bar_full[slot2]);
-        mbar_arrive_expect_tx(fb, bytes);
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.u) + (size_t)tile0 * p.tileBytes;
         const uint32_t dst = smem_u32(stages + (size_t)slot2 * p.stageBytes);
-        for (uint32_t off = 0; off < bytes; off += FUSED_COPY_CHUNK)
-            bulk_g2s(dst + off, src + off, min(FUSED_COPY_CHUNK, bytes - off), fb);
+        if (CL == 1) {
+            const uint32_t bytes = (uint32_t)ntl * p.tileBytes;     // whole tiles are contiguous
+            mbar_arrive_expect_tx(fb, bytes);
+            const unsigned char* src =
+                reinterpret_cast<const unsigned char*>(p.u) + (size_t)tile0 * p.tileBytes;
+            for (uint32_t off = 0; off < bytes; off += FUSED_COPY_CHUNK)
+                bulk_g2s(dst + off, src + off, min(FUSED_COPY_CHUNK, bytes - off), fb);
+        } else {
+            const uint32_t tb = (uint32_t)Kl * TILE_N * 8;          // this CTA's rows of each tile
+            mbar_arrive_expect_tx(fb, (uint32_t)ntl * tb);
+            for (int64_t t = 0; t < ntl; ++t)
+                bulk_g2s(dst + (uint32_t)t * tb,
+                         reinterpret_cast<const unsigned char*>(p.u) + (size_t)(tile0 + t) * p.tileBytes +
+                             (size_t)kbase * TILE_N * 8,
+                         tb, fb);
+        }
     };
     if (threadIdx.x == 0)
         for (int i = 0; i < p.NS - 1; ++i) issue(i, i, 0);
@@ -226,8 +261,8 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
         uint32_t actbits = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int k = k0 + r;
-            if (r < p.Rw && k < K && ((p.rowmask[k >> 6] >> (k & 63)) & 1ull)) actbits |= 1u << r;
+            const int k = kbase + k0 + r;
+            if (r < p.Rw && k0 + r < Kl && ((p.rowmask[k >> 6] >> (k & 63)) & 1ull)) actbits |= 1u << r;
         }
         int par = 0;
         int it = 0;
@@ -239,7 +274,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
         tr.laneBase = tabRep + lane * 8;
         int slot = 0, wrap = 0;              // it = wrap * NS + slot
         int pslot = p.NS - 1, pwrap = 0;     // ring position of stage it + NS - 1
-        for (int64_t s = blockIdx.x; s < p.nStages; s += gridDim.x, ++it) {
+        for (int64_t s = grp; s < p.nStages; s += nGroups, ++it) {
             // keep NS-1 stages in flight: stage it+NS-1 goes into the slot consumed at iteration it-1,
             // which every warp released before it could pass that iteration's denominator barrier
             if (threadIdx.x == 0) issue(it + p.NS - 1, pslot, pwrap);
@@ -251,7 +286,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                 const int tis = j * p.Wn + g;
                 const int64_t tile = s * tilesPerStage + tis;
                 if (tile >= p.nTiles) break;   // uniform over the sample group
-                const double* tp = sb + ((size_t)tis * K + k0) * TILE_N + lane;
+                const double* tp = sb + ((size_t)tis * Kl + k0) * TILE_N + lane;
                 double e[R];
                 double Dp = 0.0;
                 if (FULL) {
@@ -277,7 +312,19 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                     }
                 }
                 double D = Dp;
-                if (p.Wk > 1) {
+                if (CL == 2) {
+                    // 16 partial sums per sample: slot = owner half * 8 + warp, written locally and into
+                    // the partner CTA's shared memory; both CTAs then add them in the same order
+                    double* x = xD + (par * FUSED_MAX_CW + half * 8 + w) * 32 + lane;
+                    *x = Dp;
+                    st_cluster_f64(x, (unsigned)(half ^ 1), Dp);
+                    cluster_barrier();
+                    const double* xs = xD + par * FUSED_MAX_CW * 32 + lane;
+                    D = 0.0;
+#pragma unroll
+                    for (int ww = 0; ww < 16; ++ww) D += xs[ww * 32];
+                    par ^= 1;
+                } else if (p.Wk > 1) {
                     double* x = xD + (par * CW + g * p.Wk) * 32 + lane;
                     x[w * 32] = Dp;
                     named_bar_sync(1 + g, p.Wk * 32);
@@ -290,7 +337,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                 const double invD = valid ? 1.0 / D : 0.0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) acc[r] = fma(e[r], invD, acc[r]);
-                if (w == 0) {
+                if (w == 0 && half == 0) {
                     if (valid) {
                         logprod_push(D, mprod, esum);
                         if ((++npush & 255) == 0) logprod_renorm(mprod, esum);
@@ -306,25 +353,26 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const double t = warp_sum(acc[r]);
-            if (lane == 0 && r < p.Rw && k0 + r < K) sred[g * K + k0 + r] = t;
+            if (lane == 0 && r < p.Rw && k0 + r < Kl) sred[g * Kl + k0 + r] = t;
         }
         sumL = (double)esum * 0.693147180559945309417232 + log(mprod);
         sumL = warp_sum(sumL);
         bad = __any_sync(0xffffffffu, bad);
         if (lane == 0) {
-            s_sumL[warp] = (w == 0) ? sumL : 0.0;
+            s_sumL[warp] = (w == 0 && half == 0) ? sumL : 0.0;
             s_bad[warp] = bad;
         }
     }
+    if (CL == 2) cluster_barrier();   // the partner may not exit while it can still be written to
     __syncthreads();
 
-    double* P = p.partial + (size_t)blockIdx.x * (K + 2);
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    double* P = p.partial + (size_t)grp * (K + 2);
+    for (int k = threadIdx.x; k < Kl; k += blockDim.x) {
         double t = 0.0;
-        for (int gg = 0; gg < p.Wn; ++gg) t += sred[gg * K + k];
-        P[k] = t;
+        for (int gg = 0; gg < p.Wn; ++gg) t += sred[gg * Kl + k];
+        P[kbase + k] = t;
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && half == 0) {
         double t = 0.0;
         int b = 0;
         for (int i = 0; i < CW; ++i) {
@@ -349,7 +397,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
     double* tot = reinterpret_cast<double*>(stages);     // [K + 2] (the ring is idle now)
     for (int k = threadIdx.x; k < K + 2; k += blockDim.x) {
         double t = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) t += p.partial[(size_t)b * (K + 2) + k];
+        for (unsigned b = 0; b < nGroups; ++b) t += p.partial[(size_t)b * (K + 2) + k];
         if (k == K) t += (double)p.N * p.mid;
         tot[k] = t;
     }
@@ -428,7 +476,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
 }
 
 bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, double* midOut) {
-    if (ctx->K > 256) return false;
+    if (ctx->K > 512) return false;
     double lo = INFINITY, hi = -INFINITY;
     for (int k : ctx->active) {
         const double c = h_f[k] + ctx->h_logNk[k];
@@ -448,7 +496,6 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams
     double mid = 0.0;
     if (!fused_applicable(ctx, h_f, &mid)) return MBAR_B200_OK;
     const int K = ctx->K;
-    if (K > 256) return MBAR_B200_OK;
     FusedParams p{};
     p.K = K;
     // kernel mode (see TabRef): bit 0 = LDS-replicated exp table, bit 1 = multiplicative state constant.
@@ -466,19 +513,22 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams
     }
     const int cw = 8;
     const int rmax = 32;
+    p.CL = K > 256 ? 2 : 1;                  // 256 < K <= 512: two-CTA clusters, half the states each
+    p.Kh = p.CL == 2 ? (K + 1) / 2 : K;
     int wk = 1;
-    while (wk * rmax < K) wk *= 2;
+    while (wk * rmax < p.Kh) wk *= 2;
     p.Wk = wk;
     p.CW = cw;
     p.batch = 8;
     p.mode = mode;
     p.debugSkip = std::getenv("MBAR_B200_FUSED_SKIP") ? 1 : 0;
     p.Wn = cw / p.Wk;
-    p.Rw = (K + p.Wk - 1) / p.Wk;
-    p.tileBytes = (uint32_t)K * TILE_N * 8;
-    int tpw = (int)(65536u / (p.Wn * p.tileBytes));
+    p.Rw = (p.Kh + p.Wk - 1) / p.Wk;
+    p.tileBytes = (uint32_t)K * TILE_N * 8;                        // stride between tiles in HBM
+    const uint32_t ctaTileBytes = (uint32_t)p.Kh * TILE_N * 8;    // what one CTA pulls per tile
+    int tpw = (int)(65536u / (p.Wn * ctaTileBytes));
     p.TPW = tpw < 1 ? 1 : (tpw > 8 ? 8 : tpw);
-    p.stageBytes = (uint32_t)p.Wn * p.TPW * p.tileBytes;
+    p.stageBytes = (uint32_t)p.Wn * p.TPW * ctaTileBytes;
     const size_t header = fused_smem_header(K);
     int ns = (int)((225 * 1024 - header - ((mode & 1) ? 16384 : 0)) / p.stageBytes);
     p.NS = ns > 8 ? 8 : ns;
@@ -511,28 +561,46 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams
 // Launch with whatever c currently sits in ctx->d_c (device-resident iteration).
 int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
     const size_t smem = fused_smem_header(p.K) + (size_t)p.NS * p.stageBytes + ((p.mode & 1) ? 16384 : 0);
-    int64_t grid = p.nStages < ctx->smCount ? p.nStages : ctx->smCount;
+    int64_t grid = p.nStages < ctx->smCount / p.CL ? p.nStages : ctx->smCount / p.CL;
+    grid *= p.CL;
     const int Rt = p.Rw <= 8 ? 8 : p.Rw <= 16 ? 16 : 32;
-    const bool full = (p.Rw == Rt) && (p.K == p.Wk * p.Rw) && ((int)ctx->active.size() == p.K);
+    const bool full = (p.Rw == Rt) && (p.K == p.CL * p.Wk * p.Rw) && ((int)ctx->active.size() == p.K);
     void (*kern)(const FusedParams) = nullptr;
     int which = 0;
-#define PICK(R_, ID_)                                                                          \
-    if (Rt == R_) {                                                                            \
-        if (!full) { kern = pass_fused_kernel<R_, false, 8, 8, 0>; which = ID_; }              \
-        else if (p.mode == 0) { kern = pass_fused_kernel<R_, true, 8, 8, 0>; which = ID_ + 1; } \
-        else if (p.mode == 1) { kern = pass_fused_kernel<R_, true, 8, 8, 1>; which = ID_ + 2; } \
-        else if (p.mode == 2) { kern = pass_fused_kernel<R_, true, 8, 8, 2>; which = ID_ + 3; } \
-        else { kern = pass_fused_kernel<R_, true, 8, 8, 3>; which = ID_ + 4; }                  \
+#define PICK(R_, CL_, ID_)                                                                          \
+    if (Rt == R_ && p.CL == CL_) {                                                                  \
+        if (!full) { kern = pass_fused_kernel<R_, false, 8, 8, 0, CL_>; which = ID_; }              \
+        else if (p.mode == 0) { kern = pass_fused_kernel<R_, true, 8, 8, 0, CL_>; which = ID_ + 1; } \
+        else if (p.mode == 1) { kern = pass_fused_kernel<R_, true, 8, 8, 1, CL_>; which = ID_ + 2; } \
+        else if (p.mode == 2) { kern = pass_fused_kernel<R_, true, 8, 8, 2, CL_>; which = ID_ + 3; } \
+        else { kern = pass_fused_kernel<R_, true, 8, 8, 3, CL_>; which = ID_ + 4; }                  \
     }
-    PICK(8, 0) PICK(16, 5) PICK(32, 10)
+    PICK(8, 1, 0) PICK(16, 1, 5) PICK(32, 1, 10) PICK(32, 2, 15)
 #undef PICK
-    static size_t attrSet[16] = {0};
+    MBAR_REQUIRE(kern, MBAR_B200_ERR_INVALID, "no fused kernel variant for K=%d", p.K);
+    static size_t attrSet[20] = {0};
     if (attrSet[which] < smem) {
         MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attrSet[which] = smem;
     }
     MBAR_CUDA(cudaEventRecord(ctx->evA, ctx->stream));
-    kern<<<(unsigned)grid, p.CW * 32, smem, ctx->stream>>>(p);
+    if (p.CL == 1) {
+        kern<<<(unsigned)grid, p.CW * 32, smem, ctx->stream>>>(p);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(p.CW * 32);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        MBAR_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    }
     MBAR_CUDA(cudaEventRecord(ctx->evB, ctx->stream));
     ctx->launches++;
     ctx->passes++;

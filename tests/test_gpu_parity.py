@@ -188,3 +188,35 @@ def test_large_energy_offsets(lib):
     f = lib.mbar_solvers.solve_mbar_for_all_states(u, z["N_k"], np.zeros(K), np.arange(K),
                                                    lib.mbar_solvers.DEFAULT_SOLVER_PROTOCOL)
     np.testing.assert_allclose(f - off, z["fk_default"], atol=1e-7)
+
+
+@pytest.mark.parametrize("K,n", [(512, 12), (300, 20), (257, 8), (384, 10)])
+def test_two_cta_cluster_kernel(lib, K, n):
+    """256 < K <= 512: the fused kernel runs as clusters of two CTAs (half the states each, partial
+    denominators exchanged through distributed shared memory).  Checked against the oracle."""
+    from oracle import testsystems as ots
+
+    u, N_k = ots.oscillators(K, n, seed=100 + K)
+    N = N_k.astype(float)
+    rng = np.random.RandomState(K)
+    f = rng.normal(scale=0.5, size=K)
+    f -= f[0]
+    with lib.DeviceProblem(u, N) as p:
+        p.set_kernel("fused")
+        for mode_env in ("3", "0"):
+            import os
+            os.environ["MBAR_B200_FUSED_MODE"] = mode_env
+            S, sumL, _ = p.streaming_pass(f)
+            S_ref, L_ref = orc.single_pass_sums(u, N, f)
+            np.testing.assert_allclose(S, S_ref, rtol=1e-11)
+            np.testing.assert_allclose(sumL, L_ref.sum(), rtol=1e-12)
+        os.environ.pop("MBAR_B200_FUSED_MODE", None)
+        np.testing.assert_allclose(p.self_consistent_update(f), orc.self_consistent_update(u, N, f), atol=1e-10)
+        f5 = p.sci_iterate(np.zeros(K), 4)
+        fh = np.zeros(K)
+        for _ in range(4):
+            nxt = orc.self_consistent_update(u, N, fh)
+            fh = nxt - nxt[0]
+        np.testing.assert_allclose(f5, fh, atol=1e-10)
+        H = p.hessian(f)
+        np.testing.assert_allclose(H, orc.mbar_hessian(u, N, f), rtol=1e-9, atol=1e-10)
