@@ -60,10 +60,11 @@ struct TabRef {
     uint32_t laneBase;   // LDS mode: shared address of tab[0][lane]
 };
 
-template <int R, int B, int R0, bool PREFETCH, int MODE>
+template <int R, int B, int R0, bool PREFETCH, int MODE, bool MASKED>
 __device__ __forceinline__ void exp_batch(const double (&cu)[B], const double (&uu)[B], const TabRef tr,
                                           double (&e)[R], double& Dp, const double* nextC,
-                                          const double* nextU, double (&cn)[B], double (&un)[B]) {
+                                          const double* nextU, double (&cn)[B], double (&un)[B],
+                                          uint32_t actbits) {
     constexpr bool LDSTAB = MODE & 1, ETRICK = MODE & 2;
     double t[B], r[B], pl[B], T[B];
 #pragma unroll
@@ -126,6 +127,9 @@ __device__ __forceinline__ void exp_batch(const double (&cu)[B], const double (&
 #pragma unroll
     for (int i = 0; i < B; ++i) {
         e[R0 + i] = scale2(fma(T[i], pl[i], T[i]), __double2loint(t[i]) >> 5);
+        // rows this warp does not own (K not a multiple of the warp tiling, unsampled states) were
+        // computed on whatever bytes sit there; a select (not a multiply) discards them, NaN included
+        if (MASKED && !((actbits >> (R0 + i)) & 1u)) e[R0 + i] = 0.0;
         if (ETRICK)
             Dp = fma(cu[i], e[R0 + i], Dp);
         else
@@ -134,15 +138,16 @@ __device__ __forceinline__ void exp_batch(const double (&cu)[B], const double (&
 }
 
 // All R rows of a thread in batches of B with two alternating input register sets (no copies).
-template <int R, int B, int R0, int MODE>
+template <int R, int B, int R0, int MODE, bool MASKED>
 __device__ __forceinline__ void exp_rows(double (&cA)[B], double (&uA)[B], double (&cB)[B], double (&uB)[B],
                                          const TabRef tr, double (&e)[R], double& Dp,
-                                         const double* cbase, const double* ubase) {
+                                         const double* cbase, const double* ubase, uint32_t actbits) {
     if constexpr (R0 + B < R) {
-        exp_batch<R, B, R0, true, MODE>(cA, uA, tr, e, Dp, cbase + R0 + B, ubase + (R0 + B) * TILE_N, cB, uB);
-        exp_rows<R, B, R0 + B, MODE>(cB, uB, cA, uA, tr, e, Dp, cbase, ubase);
+        exp_batch<R, B, R0, true, MODE, MASKED>(cA, uA, tr, e, Dp, cbase + R0 + B,
+                                                ubase + (R0 + B) * TILE_N, cB, uB, actbits);
+        exp_rows<R, B, R0 + B, MODE, MASKED>(cB, uB, cA, uA, tr, e, Dp, cbase, ubase, actbits);
     } else {
-        exp_batch<R, B, R0, false, MODE>(cA, uA, tr, e, Dp, nullptr, nullptr, cB, uB);
+        exp_batch<R, B, R0, false, MODE, MASKED>(cA, uA, tr, e, Dp, nullptr, nullptr, cB, uB, actbits);
     }
 }
 
@@ -201,10 +206,12 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
     if (threadIdx.x < 32) tab[threadIdx.x] = MBAR_EXP_TABLE[threadIdx.x];
     // state constants: c_k, or E_k = exp(c_k) when the constant is applied multiplicatively
     for (int k = threadIdx.x; k < Kl; k += blockDim.x)
-        c_s[k] = (FULL && (MODE & 2)) ? exp(p.c[kbase + k]) : p.c[kbase + k];
+        c_s[k] = (MODE & 2) ? exp(p.c[kbase + k]) : p.c[kbase + k];
+    // masked variants read up to 31 state constants past this CTA's rows: keep those bytes finite
+    for (int i = threadIdx.x; i < 2 * FUSED_MAX_CW * 32; i += blockDim.x) xD[i] = 0.0;
     // lane-replicated exp table, 8 KB aligned so that its address bits never overlap the index bits
     const uint32_t tabRep = (smem_u32(stages + (size_t)p.NS * p.stageBytes) + 8191u) & ~8191u;
-    if (FULL && (MODE & 1))
+    if (MODE & 1)
         for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x)
             asm volatile("st.shared.f64 [%0], %1;" ::"r"(tabRep + i * 8), "d"(MBAR_EXP_TABLE[i >> 5]));
     if (threadIdx.x == 0) {
@@ -289,8 +296,9 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                 const double* tp = sb + ((size_t)tis * Kl + k0) * TILE_N + lane;
                 double e[R];
                 double Dp = 0.0;
-                if (FULL) {
-                    // every warp owns exactly R sampled rows: branch-free, 8 rows at a time
+                {
+                    // branch-free, 8 rows at a time; FULL: every warp owns exactly R sampled rows,
+                    // otherwise the same code runs on all R register rows and masks the foreign ones
                     constexpr int B = R < BATCH ? R : BATCH;
                     double cA[B], uA[B], cB[B], uB[B];
 #pragma unroll
@@ -298,18 +306,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                         uA[i] = lds_f64(tp + i * TILE_N);
                         cA[i] = lds_f64(c_s + k0 + i);
                     }
-                    exp_rows<R, B, 0, MODE>(cA, uA, cB, uB, tr, e, Dp, c_s + k0, tp);
-                } else {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        if ((actbits >> r) & 1u) {
-                            const double a = c_s[k0 + r] - tp[r * TILE_N];
-                            e[r] = exp_fast(a, tab);
-                            Dp += e[r];
-                        } else {
-                            e[r] = 0.0;
-                        }
-                    }
+                    exp_rows<R, B, 0, MODE, !FULL>(cA, uA, cB, uB, tr, e, Dp, c_s + k0, tp, actbits);
                 }
                 double D = Dp;
                 if (CL == 2) {
@@ -449,7 +446,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         const bool act = (p.rowmask[k >> 6] >> (k & 63)) & 1ull;
         double t = tot[k];
-        if (FULL && (MODE & 2)) t *= exp(p.c[k]);     // S_k = E_k * sum_n e0_kn / D_n / N_k
+        if ((MODE & 2) && act) t *= exp(p.c[k]);      // S_k = E_k * sum_n e0_kn / D_n / N_k
         t = act ? t / p.Nk[k] : 0.0;
         p.out[lay.S() + k] = t;
         p.out[lay.logS() + k] = 0.0;
@@ -502,6 +499,7 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams
     // MBAR_B200_FUSED_MODE overrides the default for experiments.
     int mode = 3;
     if (const char* v = std::getenv("MBAR_B200_FUSED_MODE")) mode = std::atoi(v) & 3;
+    mode |= 1;   // the shuffle-gathered table (bit 0 clear) was measured 10 % slower and is retired
     {
         double lo = INFINITY, hi = -INFINITY;
         for (int k : ctx->active) {
@@ -524,13 +522,14 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams
     p.debugSkip = std::getenv("MBAR_B200_FUSED_SKIP") ? 1 : 0;
     p.Wn = cw / p.Wk;
     p.Rw = (p.Kh + p.Wk - 1) / p.Wk;
+    p.Rw = (p.Rw + 1) & ~1;   // even: the state constants are fetched as 16-byte pairs
     p.tileBytes = (uint32_t)K * TILE_N * 8;                        // stride between tiles in HBM
     const uint32_t ctaTileBytes = (uint32_t)p.Kh * TILE_N * 8;    // what one CTA pulls per tile
     int tpw = (int)(65536u / (p.Wn * ctaTileBytes));
     p.TPW = tpw < 1 ? 1 : (tpw > 8 ? 8 : tpw);
     p.stageBytes = (uint32_t)p.Wn * p.TPW * ctaTileBytes;
     const size_t header = fused_smem_header(K);
-    int ns = (int)((225 * 1024 - header - ((mode & 1) ? 16384 : 0)) / p.stageBytes);
+    int ns = (int)((225 * 1024 - header - 16384) / p.stageBytes);
     p.NS = ns > 8 ? 8 : ns;
     if (p.NS < 2) return MBAR_B200_OK;
     const int tilesPerStage = p.Wn * p.TPW;
@@ -560,22 +559,21 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams
 
 // Launch with whatever c currently sits in ctx->d_c (device-resident iteration).
 int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
-    const size_t smem = fused_smem_header(p.K) + (size_t)p.NS * p.stageBytes + ((p.mode & 1) ? 16384 : 0);
+    const size_t smem = fused_smem_header(p.K) + (size_t)p.NS * p.stageBytes + 16384;
     int64_t grid = p.nStages < ctx->smCount / p.CL ? p.nStages : ctx->smCount / p.CL;
     grid *= p.CL;
     const int Rt = p.Rw <= 8 ? 8 : p.Rw <= 16 ? 16 : 32;
     const bool full = (p.Rw == Rt) && (p.K == p.CL * p.Wk * p.Rw) && ((int)ctx->active.size() == p.K);
     void (*kern)(const FusedParams) = nullptr;
     int which = 0;
-#define PICK(R_, CL_, ID_)                                                                          \
-    if (Rt == R_ && p.CL == CL_) {                                                                  \
-        if (!full) { kern = pass_fused_kernel<R_, false, 8, 8, 0, CL_>; which = ID_; }              \
-        else if (p.mode == 0) { kern = pass_fused_kernel<R_, true, 8, 8, 0, CL_>; which = ID_ + 1; } \
-        else if (p.mode == 1) { kern = pass_fused_kernel<R_, true, 8, 8, 1, CL_>; which = ID_ + 2; } \
-        else if (p.mode == 2) { kern = pass_fused_kernel<R_, true, 8, 8, 2, CL_>; which = ID_ + 3; } \
-        else { kern = pass_fused_kernel<R_, true, 8, 8, 3, CL_>; which = ID_ + 4; }                  \
+#define PICK(R_, CL_, ID_)                                                                           \
+    if (Rt == R_ && p.CL == CL_) {                                                                   \
+        if (!full && !(p.mode & 2)) { kern = pass_fused_kernel<R_, false, 8, 8, 1, CL_>; which = ID_; } \
+        else if (!full) { kern = pass_fused_kernel<R_, false, 8, 8, 3, CL_>; which = ID_ + 1; }        \
+        else if (!(p.mode & 2)) { kern = pass_fused_kernel<R_, true, 8, 8, 1, CL_>; which = ID_ + 2; } \
+        else { kern = pass_fused_kernel<R_, true, 8, 8, 3, CL_>; which = ID_ + 3; }                    \
     }
-    PICK(8, 1, 0) PICK(16, 1, 5) PICK(32, 1, 10) PICK(32, 2, 15)
+    PICK(8, 1, 0) PICK(16, 1, 4) PICK(32, 1, 8) PICK(32, 2, 12)
 #undef PICK
     MBAR_REQUIRE(kern, MBAR_B200_ERR_INVALID, "no fused kernel variant for K=%d", p.K);
     static size_t attrSet[20] = {0};
