@@ -124,7 +124,7 @@ def measured_peak():
 def ncu_traffic(K, N_local):
     """dram read+write bytes per launch of the fused kernel from the committed ncu capture, scaled
     to this launch's size when the capture was taken at a smaller N of the same K."""
-    path = os.path.join(ROOT, "profiles", "fused_pass_traffic.json")
+    path = os.path.join(ROOT, "profiles", "fused_pass_c3_r1.json")
     try:
         t = json.load(open(path))
         if t["K"] == K:
@@ -342,7 +342,7 @@ def run_ours(args):
                        "wall_s_rank0": wall},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(K, N_local),
-                         "kernel": "pass_fused_kernel<32,true,8,8>",
+                         "kernel": "pass_fused_kernel<R=32, FULL, 8 warps, batch 8, MODE 3 (LDS table + multiplicative constant), CL=1>",
                          "algorithmic_bytes_per_launch": 8 * K * N_local,
                          "launch_ms": kern_ms_per_launch, "peak_source": peak_src,
                          "how": "per-launch cudaEvent pairs recorded around the kernel inside the timed loop"},
