@@ -1,26 +1,31 @@
-// Fused streaming pass for K <= 256 sampled+unsampled rows: ONE read of u_kn per iteration.
+// Fused streaming pass, K <= 512: ONE read of u_kn per solver iteration.
 //
 // Reference being replaced: the two logsumexp sweeps of self_consistent_update / mbar_gradient /
 // mbar_objective (mbar_solvers.py:231-242, :284-292, :327-355).  One launch yields S_k = sum_n W_nk and
-// sum_n L_n, from which  f_sci = f - log S,  g = N (S - 1),  obj = sum L - N.f  all follow.
+// sum_n L_n, from which  f_sci = f - log S,  g = N (S - 1),  obj = sum L - N.f  all follow; in the
+// device-resident iteration the launch also exchanges the sums with the other GPUs and applies the update.
 //
-// Structure (persistent, one CTA per SM, 8 consumer warps + 1 producer warp):
-//   * producer lane streams whole stages (contiguous extents of the tile-major layout) into a
-//     3..8-deep shared-memory ring with cp.async.bulk (TMA engine) completing on mbarriers;
-//   * consumers: lane = sample, warp = contiguous chunk of <= R states.  Each thread pulls its
-//     R energies out of shared memory ONCE, does one fp64 exp per entry with the binary exponent
-//     handled on the integer pipe, and keeps R per-state accumulators in registers for the whole
-//     kernel — no shuffles, no atomics, no re-reads in the steady state;
-//   * the per-sample denominator is exchanged between the Wk warps that share a sample group through
-//     4 KB of shared memory and one named barrier per tile (none when K <= 32);
-//   * per-CTA partials -> global, last CTA (ticket) reduces them in CTA order: deterministic.
+// Structure (persistent, one CTA of 8 warps per SM; clusters of two CTAs when 256 < K <= 512):
+//   * thread 0 streams whole stages (contiguous extents of the tile-major layout) into a 3..8-deep
+//     shared-memory ring with cp.async.bulk (TMA engine, SASS UBLKCP) completing on mbarriers.  There is
+//     no producer warp: a 9th warp would cap every thread at 168 registers instead of 255;
+//   * lane = sample, warp = contiguous chunk of <= R states.  Each thread pulls its R energies out of
+//     shared memory ONCE, does one fp64 exp per entry (table entry from a lane-replicated 8 KB table,
+//     binary exponent on the integer pipe) and keeps R per-state accumulators in registers for the whole
+//     kernel: no shuffles, no atomics, no re-reads in the steady state;
+//   * the per-sample denominator is exchanged between the Wk warps of a sample group through 4 KB of
+//     shared memory + one named barrier per tile (none when K <= 32); between the two CTAs of a cluster
+//     through distributed shared memory + one cluster barrier per tile;
+//   * per-CTA partials -> global; the last CTA (ticket) reduces them in CTA order (deterministic),
+//     optionally gathers the other GPUs' sums through peer memory and applies the K-vector update.
 //
 // No per-sample max is needed: samples are pre-shifted so that min over sampled k of u'_kn = 0, hence
 // max_k (c_k - u'_kn) lies in [min c, max c]; with c centred on `mid` and max c - min c < 1200 every
 // exponent stays inside the fp64 range.  The kernel still verifies D_n per sample and raises a flag
 // (host falls back to the generic kernel) if that assumption is ever violated.
 //
-// fp64 pipe budget per (k, n) entry: 1 (c - u) + 9 (exp) + 1 (D +=) + 1 (acc FMA) = 12 ops.
+// fp64-pipe budget per (k, n) entry: 9 (exp) + 1 (D) + 1 (accumulate) = 11 when the state constant is
+// applied multiplicatively (spread(c) <= 600), 12 otherwise.  See DESIGN.md 3.1 for measurements.
 #include <cmath>
 #include <cstdlib>
 
