@@ -133,6 +133,11 @@ int mbar_b200_hessian(mbar_b200_ctx* ctx, const double* f_k, double* H_out);
  * row stride ld_out elements; exponentiate != 0 gives mbar_W_nk (mbar_solvers.py:476-507). */
 int mbar_b200_log_W_nk(mbar_b200_ctx* ctx, const double* f_k, double* logW_host, int64_t ld_out,
                        int exponentiate);
+/* Sums and second moments of the weights of ALL K states (sampled or not) at f_k:
+ *   S[K] = sum_n W_nk,  G[K*K] = W^T W.
+ * Everything MBAR's asymptotic covariance (mbar.py:1837-1858, "svd-ew"), compute_overlap (mbar.py:605-606) and
+ * compute_effective_sample_number (mbar.py:546-549) need, without materialising the N x K weight matrix. */
+int mbar_b200_weight_moments(mbar_b200_ctx* ctx, const double* f_k, double* S_out, double* G_out);
 /* Per-sample log denominators L_n [N_local] (the logsumexp at mbar_solvers.py:238). */
 int mbar_b200_log_denominator(mbar_b200_ctx* ctx, const double* f_k, double* L_host);
 

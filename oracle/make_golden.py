@@ -98,6 +98,19 @@ def case(name, u_kn, N_k, store_u, regen, rng):
             data[f"{tag}_{k}"] = v
     for pname, fk in solve_all(u_kn, N_k).items():
         data[f"fk_{pname}"] = fk
+    if K <= 64:
+        # estimators of SURVEY 8f N1 at the converged default solution (mbar.py:620, :563, :496)
+        m = pymbar.MBAR(u_kn, N_k)
+        r = m.compute_free_energy_differences(uncertainty_method="svd-ew", return_theta=True)
+        data["est_dDelta_f"] = np.array(r["dDelta_f"])
+        data["est_Theta"] = np.array(r["Theta"])
+        data["est_Delta_f"] = np.array(r["Delta_f"])
+        ov = m.compute_overlap()
+        data["est_overlap_matrix"] = np.array(ov["matrix"])
+        data["est_overlap_scalar"] = np.float64(np.real(ov["scalar"]))
+        data["est_N_eff"] = np.array(m.compute_effective_sample_number())
+        W = np.exp(m.Log_W_nk)
+        data["est_G"] = W.T @ W
     # adaptive trajectory from f=0 on sampled states (mbar_solvers.py:510-667), tol 1e-12
     sampled = N_k > 0
     us = ref.precondition_u_kn(u_kn[sampled], 1.0 * N_k[sampled], np.zeros(sampled.sum()))

@@ -111,6 +111,7 @@ struct PassWant {
     bool L = false;          // keep per-sample L'_n on the device
     bool unsampled = false;  // need log-domain sums for N_k == 0 states
     bool G = false;          // K x K second moments
+    bool Gall = false;       // ... including the unsampled states' rows and columns
 };
 
 static int check_range(mbar_b200_ctx* c, const double* f) {
@@ -131,7 +132,7 @@ static int run_pass(mbar_b200_ctx* c, const double* f, PassWant want) {
     const int K = c->K;
     const PassLayout lay{K};
     const bool needUnsampled = want.unsampled && (int)c->active.size() < K;
-    const bool wantL = want.L || want.G;
+    const bool wantL = want.L || want.G || want.Gall;
     // attempt 0: fused (if applicable) | 1: generic, linear sums | 2: generic, log-domain sums for
     // every state (the reference's second logsumexp, mbar_solvers.py:240): taken when a sampled
     // state's S_k underflows, i.e. f_k is hundreds of kT away from self-consistency.
@@ -176,8 +177,8 @@ static int run_pass(mbar_b200_ctx* c, const double* f, PassWant want) {
         if (!underflow) break;
         if (attempt == 0) ++attempt;   // skip the linear generic pass: it would underflow the same way
     }
-    if (want.G) {
-        MBAR_TRY(launch_hessian(c, f));
+    if (want.G || want.Gall) {
+        MBAR_TRY(launch_hessian(c, f, want.Gall));
         MBAR_TRY(comm_allreduce(c, c->d_out + lay.G(), K * K, 0));
         MBAR_CUDA(cudaMemcpyAsync(c->h_out + lay.G(), c->d_out + lay.G(), (size_t)K * K * sizeof(double),
                                   cudaMemcpyDeviceToHost, c->stream));
@@ -308,6 +309,26 @@ int mbar_b200_hessian(mbar_b200_ctx* c, const double* f, double* H) {
             if (i == j) v += c->h_Nk[i] * c->h_out[lay.S() + i];
             H[(size_t)i * K + j] = (c->h_Nk[i] > 0 && c->h_Nk[j] > 0) ? v : 0.0;
         }
+    return MBAR_B200_OK;
+}
+
+int mbar_b200_weight_moments(mbar_b200_ctx* c, const double* f, double* S, double* G) {
+    MBAR_REQUIRE(G, MBAR_B200_ERR_INVALID, "G_out is NULL");
+    PassWant w;
+    w.unsampled = true;
+    w.Gall = true;
+    MBAR_TRY(run_pass(c, f, w));
+    const int K = c->K;
+    const PassLayout lay{K};
+    const double* Gh = c->h_out + lay.G();
+    for (int i = 0; i < K; ++i) {
+        const double si = c->h_Nk[i] > 0 ? c->h_Nk[i] : 1.0;
+        if (S) S[i] = c->h_Nk[i] > 0 ? c->h_out[lay.S() + i] : std::exp(c->h_out[lay.logS() + i]);
+        for (int j = 0; j < K; ++j) {
+            const double sj = c->h_Nk[j] > 0 ? c->h_Nk[j] : 1.0;
+            G[(size_t)i * K + j] = Gh[(size_t)i * K + j] / (si * sj);
+        }
+    }
     return MBAR_B200_OK;
 }
 

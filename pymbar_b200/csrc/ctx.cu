@@ -336,6 +336,7 @@ int mbar_b200_create(mbar_b200_ctx** out, int device, int32_t K, int64_t N_local
     ALLOC(c->d_Nk, (size_t)K * sizeof(double));
     ALLOC(c->d_rowmask, mask.size() * sizeof(unsigned long long));
     ALLOC(c->d_zeromask, mask.size() * sizeof(unsigned long long));
+    ALLOC(c->d_onesmask, mask.size() * sizeof(unsigned long long));
     ALLOC(c->d_partial, (size_t)MAX_GRID * (3 * (size_t)K + 2) * sizeof(double));
     ALLOC(c->d_out, (size_t)lay.size(true) * sizeof(double));
     ALLOC(c->d_ticket, 4 * sizeof(unsigned int));
@@ -355,6 +356,7 @@ int mbar_b200_create(mbar_b200_ctx** out, int device, int32_t K, int64_t N_local
     MBAR_CUDA(cudaMemcpy(c->d_rowmask, mask.data(), mask.size() * sizeof(unsigned long long),
                          cudaMemcpyHostToDevice));
     MBAR_CUDA(cudaMemset(c->d_zeromask, 0, mask.size() * sizeof(unsigned long long)));
+    MBAR_CUDA(cudaMemset(c->d_onesmask, 0xff, mask.size() * sizeof(unsigned long long)));
     MBAR_CUDA(cudaMemset(c->d_ticket, 0, 4 * sizeof(unsigned int)));
     MBAR_CUDA(cudaMemset(c->d_flag, 0, 4 * sizeof(int)));
     *out = c;
@@ -369,7 +371,7 @@ int mbar_b200_destroy(mbar_b200_ctx* c) {
     cudaFree(c->d_inbox);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_u); cudaFree(c->d_xshift); cudaFree(c->d_c); cudaFree(c->d_Nk);
-    cudaFree(c->d_rowmask); cudaFree(c->d_zeromask); cudaFree(c->d_partial); cudaFree(c->d_out); cudaFree(c->d_L);
+    cudaFree(c->d_rowmask); cudaFree(c->d_zeromask); cudaFree(c->d_onesmask); cudaFree(c->d_partial); cudaFree(c->d_out); cudaFree(c->d_L);
     cudaFree(c->d_W); cudaFree(c->d_ticket); cudaFree(c->d_flag); cudaFree(c->d_f);
     cudaFree(c->d_scratch);
     for (int i = 0; i < 2; ++i) {

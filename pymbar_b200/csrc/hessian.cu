@@ -38,7 +38,7 @@ __device__ __forceinline__ void convert_row(double* P, int row, int lane, double
     const double v = P[row * TILE_N + lane];
     __syncwarp();   // every lane has read the row before any lane overwrites a permuted slot of it
     double wv = 0.0;
-    if (valid && act) wv = exp_fast(fmax(ck - v - L, -800.0), tab);
+    if (valid && act) wv = exp_fast(fmin(fmax(ck - v - L, -800.0), 700.0), tab);
     P[row * TILE_N + (lane ^ ((row & 7) << 2))] = wv;
 }
 
@@ -204,11 +204,12 @@ hessian_reduce_kernel(const double* __restrict__ Gpart, int K, int nPairs, int n
 }
 
 // Requires ctx->d_L (shifted-frame L'_n) from the preceding pass at the same f.
-int launch_hessian(mbar_b200_ctx* ctx, const double* h_f) {
+int launch_hessian(mbar_b200_ctx* ctx, const double* h_f, bool allRows) {
     const int K = ctx->K;
     MBAR_REQUIRE(ctx->d_L, MBAR_B200_ERR_NOT_READY, "hessian: per-sample L not available");
+    // sampled rows carry N_k W_nk (c = f + log N); with allRows the unsampled rows carry W_nk (c = f)
     for (int k = 0; k < K; ++k)
-        ctx->h_f[2 * K + k] = std::isinf(ctx->h_logNk[k]) ? 0.0 : h_f[k] + ctx->h_logNk[k];
+        ctx->h_f[2 * K + k] = std::isinf(ctx->h_logNk[k]) ? (allRows ? h_f[k] : 0.0) : h_f[k] + ctx->h_logNk[k];
     MBAR_CUDA(cudaMemcpyAsync(ctx->d_c + 2 * K, ctx->h_f + 2 * K, (size_t)K * sizeof(double),
                               cudaMemcpyHostToDevice, ctx->stream));
     const int nB = (K + HB - 1) / HB;
@@ -226,7 +227,8 @@ int launch_hessian(mbar_b200_ctx* ctx, const double* h_f) {
     }
     const PassLayout lay{K};
     hessian_kernel<<<dim3(nPairs, nChunks), 512, smem, ctx->stream>>>(
-        ctx->d_u, ctx->d_L, ctx->d_c + 2 * K, ctx->d_rowmask, K, ctx->N, ctx->nTiles, nChunks, ctx->d_W);
+        ctx->d_u, ctx->d_L, ctx->d_c + 2 * K, allRows ? ctx->d_onesmask : ctx->d_rowmask, K, ctx->N, ctx->nTiles,
+        nChunks, ctx->d_W);
     MBAR_CUDA(cudaGetLastError());
     hessian_reduce_kernel<<<dim3(nPairs, 16), 256, 0, ctx->stream>>>(ctx->d_W, K, nPairs, nChunks,
                                                                     ctx->d_out + lay.G());

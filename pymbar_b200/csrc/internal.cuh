@@ -84,6 +84,7 @@ struct mbar_b200_ctx {
     double* d_Nk = nullptr;         // [K]
     unsigned long long* d_rowmask = nullptr;  // [ceil(K/64)] bit per sampled state
     unsigned long long* d_zeromask = nullptr; // same size, all zero (log-domain for every row)
+    unsigned long long* d_onesmask = nullptr; // same size, all one (second moments of every state)
     double* d_partial = nullptr;    // [MAX_GRID][K+2] per-CTA partials
     double* d_out = nullptr;        // PassLayout packed result (with G)
     double* h_out = nullptr;        // pinned mirror of d_out
@@ -151,7 +152,7 @@ int launch_pass_fused(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool* u
 int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams* out, bool* ok);
 int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p);
 bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, double* midOut);
-int launch_hessian(mbar_b200_ctx* ctx, const double* h_f);
+int launch_hessian(mbar_b200_ctx* ctx, const double* h_f, bool allRows);
 int launch_logw(mbar_b200_ctx* ctx, const double* h_f, double* logW_host, int64_t ld, int expo);
 int launch_synth(mbar_b200_ctx* ctx, const mbar_b200_synth* spec);
 int launch_untile(mbar_b200_ctx* ctx, int64_t n0, int64_t n, double* d_dst, int64_t ld);

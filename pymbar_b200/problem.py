@@ -222,6 +222,14 @@ class DeviceProblem:
         check(self._lib.mbar_b200_hessian(self._h, _dptr(f), _dptr(H)))
         return H
 
+    def weight_moments(self, f_k):
+        """(S_k, G = W^T W) over ALL states — the K x K input of pymbar_b200.estimators."""
+        f = _f64(f_k, self.K)
+        S = np.empty(self.K)
+        G = np.empty((self.K, self.K))
+        check(self._lib.mbar_b200_weight_moments(self._h, _dptr(f), _dptr(S), _dptr(G)))
+        return S, G
+
     def log_W_nk(self, f_k, exponentiate=False, out=None):
         f = _f64(f_k, self.K)
         if out is None:
