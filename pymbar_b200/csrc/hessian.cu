@@ -220,10 +220,10 @@ int launch_hessian(mbar_b200_ctx* ctx, const double* h_f, bool allRows) {
     const size_t partBytes = (size_t)nChunks * nPairs * HB * HB * sizeof(double);
     if (!ctx->d_W) MBAR_CUDA(cudaMalloc((void**)&ctx->d_W, partBytes));
     const size_t smem = 512 + (size_t)HNS * 2 * HPANEL;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[16] = {false};
+    if (!attr[ctx->device & 15]) {
         MBAR_CUDA(cudaFuncSetAttribute(hessian_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+        attr[ctx->device & 15] = true;
     }
     const PassLayout lay{K};
     hessian_kernel<<<dim3(nPairs, nChunks), 512, smem, ctx->stream>>>(

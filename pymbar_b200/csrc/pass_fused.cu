@@ -581,7 +581,8 @@ int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
     PICK(8, 1, 0) PICK(16, 1, 4) PICK(32, 1, 8) PICK(32, 2, 12)
 #undef PICK
     MBAR_REQUIRE(kern, MBAR_B200_ERR_INVALID, "no fused kernel variant for K=%d", p.K);
-    static size_t attrSet[20] = {0};
+    static size_t attrSetAll[16][20] = {{0}};          // per device: the attribute belongs to the context
+    size_t* attrSet = attrSetAll[ctx->device & 15];
     if (attrSet[which] < smem) {
         MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attrSet[which] = smem;

@@ -220,3 +220,31 @@ def test_two_cta_cluster_kernel(lib, K, n):
         np.testing.assert_allclose(f5, fh, atol=1e-10)
         H = p.hessian(f)
         np.testing.assert_allclose(H, orc.mbar_hessian(u, N, f), rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("K,N_k", [(1, [5]), (2, [1, 2]), (3, [1, 0, 1]), (2, [40, 0]), (7, [3] * 7), (33, [2] * 33),
+                                   (5, [31, 1, 0, 0, 1]), (4, [32, 32, 32, 32])])
+def test_tiny_and_ragged_shapes(lib, K, N_k):
+    """Degenerate sizes: a single state, fewer than 32 samples (one partial tile), exactly one tile,
+    N_k = 0 in various places.  Every primitive against the oracle."""
+    rng = np.random.RandomState(K * 100 + sum(N_k))
+    N_k = np.array(N_k)
+    N = int(N_k.sum())
+    u = rng.normal(size=(K, N)) * 3 + rng.normal(size=(K, 1)) * 5
+    Nf = N_k.astype(float)
+    s = Nf > 0
+    f = rng.normal(size=K)
+    f -= f[0]
+    for kern in ("fused", "generic"):
+        with lib.DeviceProblem(u, Nf) as p:
+            p.set_kernel(kern)
+            np.testing.assert_allclose(p.self_consistent_update(f), orc.self_consistent_update(u, Nf, f), atol=1e-10)
+            np.testing.assert_allclose(p.gradient(f)[s], orc.mbar_gradient(u[s], Nf[s], f[s]), rtol=1e-10, atol=1e-9)
+            np.testing.assert_allclose(p.objective(f), orc.mbar_objective(u[s], Nf[s], f[s]), rtol=1e-11, atol=1e-9)
+            np.testing.assert_allclose(p.hessian(f)[np.ix_(s, s)], orc.mbar_hessian(u[s], Nf[s], f[s]), rtol=1e-9, atol=1e-10)
+            np.testing.assert_allclose(p.log_W_nk(f), orc.mbar_log_W_nk(u, Nf, f), atol=1e-10)
+    sws = np.where(N_k != 0)[0]
+    proto = tuple(dict(st) for st in lib.mbar_solvers.DEFAULT_SOLVER_PROTOCOL)
+    got = lib.mbar_solvers.solve_mbar_for_all_states(u, N_k, np.zeros(K), sws, proto)
+    want = orc.solve_mbar_for_all_states(u, N_k, np.zeros(K), sws, orc.DEFAULT_SOLVER_PROTOCOL)
+    np.testing.assert_allclose(got, want, atol=1e-8)
