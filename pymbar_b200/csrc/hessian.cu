@@ -42,10 +42,18 @@ __device__ __forceinline__ void convert_row(double* P, int row, int lane, double
     P[row * TILE_N + (lane ^ ((row & 7) << 2))] = wv;
 }
 
+// Work split: CTAs [pairStart[p], pairStart[p+1]) own block pair p and share its tiles evenly.  Diagonal
+// pairs only multiply the 10 lower-triangular 32 x 32 sub-blocks (3 instead of 4 per scheduler), so
+// they get 3/4 of the CTAs an off-diagonal pair gets.
+struct HessSplit {
+    int nPairs;
+    int pairStart[40];
+};
+
 __global__ void __launch_bounds__(512, 1)
 hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
                const double* __restrict__ c, const unsigned long long* __restrict__ rowmask, int K,
-               int64_t N, int64_t nTiles, int nChunks, double* __restrict__ Gpart) {
+               int64_t N, int64_t nTiles, const HessSplit split, double* __restrict__ Gpart) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* tab = reinterpret_cast<double*>(smem_raw);                      // [32]
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(tab + 32);             // [HNS]
@@ -53,11 +61,14 @@ hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
     unsigned char* ring = smem_raw + 512;                                   // [HNS][2][HPANEL]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;             // 16 warps
 
-    int bi = 0, rem = blockIdx.x;                 // pairs enumerated (0,0),(1,0),(1,1),(2,0),...
+    int pair = 0;
+    while (pair + 1 < split.nPairs && (int)blockIdx.x >= split.pairStart[pair + 1]) ++pair;
+    const int chunk = blockIdx.x - split.pairStart[pair];
+    const int nChunks = split.pairStart[pair + 1] - split.pairStart[pair];
+    int bi = 0, rem = pair;                       // pairs enumerated (0,0),(1,0),(1,1),(2,0),...
     while (rem > bi) { rem -= bi + 1; ++bi; }
     const int bj = rem;
     const bool diag = (bi == bj);
-    const int chunk = blockIdx.y;
     const int64_t t0 = nTiles * chunk / nChunks, t1 = nTiles * (chunk + 1) / nChunks;
     const int rowsI = min(HB, K - bi * HB), rowsJ = min(HB, K - bj * HB);
 
@@ -90,8 +101,18 @@ hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
     }
 
     // conversion (vector fp64 pipe): warp owns rows warp*8 .. +7 of each panel, lane = sample.
-    // MMA (tensor pipe): warp tile 32 (i) x 32 (j): wm = warp / 4, wn = warp % 4.
-    const int wm = warp >> 2, wn = warp & 3;
+    // MMA (tensor pipe): warp tile 32 (i) x 32 (j).  Off-diagonal pair: wm = warp / 4, wn = warp % 4.
+    // Diagonal pair: only the 10 sub-blocks with wm >= wn are needed (Ghat is symmetric); warps 0..9 take
+    // them, which loads the four schedulers 3/3/2/2 instead of 4/4/4/4, warps 10..15 only convert.
+    int wm = warp >> 2, wn = warp & 3;
+    bool mmaWarp = true;
+    if (diag) {
+        mmaWarp = warp < 10;
+        int t = warp < 10 ? warp : 0;
+        wm = 0;
+        while (t > wm) { t -= wm + 1; ++wm; }     // triangular enumeration (0,0),(1,0),(1,1),(2,0),...
+        wn = t;
+    }
     double acc[4][4][2];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -154,6 +175,7 @@ hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
                 convert_row(Ni, warp * 8 + ks, lane, cI[ks], (actI >> ks) & 1u, validN, Ln, tab);
                 if (!diag) convert_row(Nj, warp * 8 + ks, lane, cJ[ks], (actJ >> ks) & 1u, validN, Ln, tab);
             }
+            if (!mmaWarp) continue;
             const int col = ((ks ^ fragRow) << 2) + fragCol;      // (4 ks + fragCol) ^ (fragRow << 2)
             double a[4], b[4];
 #pragma unroll
@@ -171,8 +193,8 @@ hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
         __syncthreads();            // next tile's weights are complete for every warp
     }
     // write this CTA's 128 x 128 partial block: Gpart[chunk][pair][128][128]
-    const int nPairs = gridDim.x;
-    double* out = Gpart + ((size_t)chunk * nPairs + blockIdx.x) * HB * HB;
+    double* out = Gpart + (size_t)blockIdx.x * HB * HB;
+    if (mmaWarp)
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
@@ -184,22 +206,24 @@ hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
         }
 }
 
-// Sum partial blocks over chunks (in order) and scatter to the full symmetric K x K matrix.
+// Sum the partial blocks of each pair over its CTAs (in order: deterministic) and scatter to the full
+// symmetric K x K matrix.  Diagonal pairs only hold sub-blocks with row-block >= column-block.
 __global__ void __launch_bounds__(256)
-hessian_reduce_kernel(const double* __restrict__ Gpart, int K, int nPairs, int nChunks,
-                      double* __restrict__ G) {
+hessian_reduce_kernel(const double* __restrict__ Gpart, int K, const HessSplit split, double* __restrict__ G) {
     const int pair = blockIdx.x;
     int bi = 0, rem = pair;
     while (rem > bi) { rem -= bi + 1; ++bi; }
     const int bj = rem;
+    const int c0 = split.pairStart[pair], c1 = split.pairStart[pair + 1];
     for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < HB * HB; e += gridDim.y * blockDim.x) {
         const int r = e / HB, cidx = e % HB;
         const int i = bi * HB + r, j = bj * HB + cidx;
         if (i >= K || j >= K) continue;
+        if (bi == bj && (r >> 5) < (cidx >> 5)) continue;      // filled by its mirror image below
         double s = 0.0;
-        for (int ch = 0; ch < nChunks; ++ch) s += Gpart[((size_t)ch * nPairs + pair) * HB * HB + e];
+        for (int ch = c0; ch < c1; ++ch) s += Gpart[(size_t)ch * HB * HB + e];
         G[(size_t)i * K + j] = s;
-        if (bi != bj) G[(size_t)j * K + i] = s;
+        if (bi != bj || (r >> 5) > (cidx >> 5)) G[(size_t)j * K + i] = s;
     }
 }
 
@@ -214,11 +238,33 @@ int launch_hessian(mbar_b200_ctx* ctx, const double* h_f, bool allRows) {
                               cudaMemcpyHostToDevice, ctx->stream));
     const int nB = (K + HB - 1) / HB;
     const int nPairs = nB * (nB + 1) / 2;
-    int nChunks = ctx->smCount / nPairs;
-    if (nChunks < 1) nChunks = 1;
-    if ((int64_t)nChunks > ctx->nTiles) nChunks = (int)ctx->nTiles;
-    const size_t partBytes = (size_t)nChunks * nPairs * HB * HB * sizeof(double);
-    if (!ctx->d_W) MBAR_CUDA(cudaMalloc((void**)&ctx->d_W, partBytes));
+    MBAR_REQUIRE(nPairs < 40, MBAR_B200_ERR_INVALID, "K=%d too large for the Hessian kernel (K <= 1024)", K);
+    // CTAs per pair proportional to its cost per tile (4 for off-diagonal, 3 for diagonal pairs)
+    HessSplit split{};
+    split.nPairs = nPairs;
+    {
+        double wsum = 0.0;
+        for (int bi = 0, p = 0; bi < nB; ++bi)
+            for (int bj = 0; bj <= bi; ++bj, ++p) wsum += (bi == bj) ? 3.0 : 4.0;
+        int total = ctx->smCount > nPairs ? ctx->smCount : nPairs;
+        int used = 0;
+        for (int bi = 0, p = 0; bi < nB; ++bi)
+            for (int bj = 0; bj <= bi; ++bj, ++p) {
+                int n = (int)(total * ((bi == bj) ? 3.0 : 4.0) / wsum);
+                if (n < 1) n = 1;
+                if ((int64_t)n > ctx->nTiles) n = (int)ctx->nTiles;
+                split.pairStart[p] = used;
+                used += n;
+            }
+        split.pairStart[nPairs] = used;
+    }
+    const int nCtas = split.pairStart[nPairs];
+    const size_t partBytes = (size_t)nCtas * HB * HB * sizeof(double);
+    if (!ctx->d_W) {
+        // sized for the larger of the two row selections (identical split for both)
+        MBAR_CUDA(cudaMalloc((void**)&ctx->d_W, partBytes));
+        MBAR_CUDA(cudaMemset(ctx->d_W, 0, partBytes));
+    }
     const size_t smem = 512 + (size_t)HNS * 2 * HPANEL;
     static bool attr[16] = {false};
     if (!attr[ctx->device & 15]) {
@@ -226,12 +272,11 @@ int launch_hessian(mbar_b200_ctx* ctx, const double* h_f, bool allRows) {
         attr[ctx->device & 15] = true;
     }
     const PassLayout lay{K};
-    hessian_kernel<<<dim3(nPairs, nChunks), 512, smem, ctx->stream>>>(
+    hessian_kernel<<<nCtas, 512, smem, ctx->stream>>>(
         ctx->d_u, ctx->d_L, ctx->d_c + 2 * K, allRows ? ctx->d_onesmask : ctx->d_rowmask, K, ctx->N, ctx->nTiles,
-        nChunks, ctx->d_W);
+        split, ctx->d_W);
     MBAR_CUDA(cudaGetLastError());
-    hessian_reduce_kernel<<<dim3(nPairs, 16), 256, 0, ctx->stream>>>(ctx->d_W, K, nPairs, nChunks,
-                                                                    ctx->d_out + lay.G());
+    hessian_reduce_kernel<<<dim3(nPairs, 16), 256, 0, ctx->stream>>>(ctx->d_W, K, split, ctx->d_out + lay.G());
     MBAR_CUDA(cudaGetLastError());
     ctx->launches += 2;
     ctx->passes++;
