@@ -273,6 +273,16 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     achieved = 8.0 * K * N_local / (kern_ms_per_launch * 1e-3) / 1e9
 
+    # a real solve on the same data (not part of the timed region): adaptive Newton/self-consistent
+    # solver of mbar_solvers.py:510-667 from f = 0 to tol 1e-12 (C3: "Newton-Raphson with K x K Hessian")
+    barrier()
+    t0 = time.perf_counter()
+    f_solved, solve_info = prob.solve_adaptive(np.zeros(K), tol=1e-12, maxiter=100, min_sc_iter=0)
+    solve_wall = time.perf_counter() - t0
+    adaptive_solve = {k: solve_info[k] for k in ("success", "iterations", "nr_iterations", "sci_iterations",
+                                                 "passes", "hessian_passes", "gnorm", "device_ms")}
+    adaptive_solve["wall_s"] = solve_wall
+
     # parity spot check of the timed state against the CPU oracle on a slice (not timed)
     parity = None
     if rank == 0:
@@ -351,6 +361,7 @@ def run_ours(args):
                              "sample": f"numpy oracle self_consistent_update on K={K}, N={n_sample} of the same "
                                        f"family ({cpu_step:.2f} s/step); reference is single-threaded numpy"},
             "e2e": e2e,
+            "adaptive_solve": adaptive_solve,
             "gpu_launches": c1["launches"] - c0["launches"],
             "clocks": clocks,
             "parity_S_rel_err_vs_oracle_slice": parity,
