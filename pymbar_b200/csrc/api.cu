@@ -140,8 +140,8 @@ static int run_pass(mbar_b200_ctx* c, const double* f, PassWant want) {
     for (int attempt = 0; attempt < 3; ++attempt) {
         fused = false;
         const bool logAll = (attempt == 2);
-        if (attempt == 0 && c->kernelChoice != MBAR_B200_KERNEL_GENERIC && !needUnsampled)
-            MBAR_TRY(launch_pass_fused(c, f, wantL, &fused));
+        if (attempt == 0 && c->kernelChoice != MBAR_B200_KERNEL_GENERIC)
+            MBAR_TRY(launch_pass_fused(c, f, wantL, needUnsampled, &fused));
         if (attempt == 0 && !fused) continue;
         if (!fused) MBAR_TRY(launch_pass_generic(c, f, wantL, logAll));
         // S | sumL | flag are sums over samples -> one all-reduce
@@ -164,6 +164,19 @@ static int run_pass(mbar_b200_ctx* c, const double* f, PassWant want) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->evA, c->evB) == cudaSuccess) c->lastPassMs = ms;
         if (fused && c->h_out[lay.flag()] != 0.0) continue;   // range assumption failed on a sample
+        if (fused && needUnsampled) {
+            // unsampled states rode along with weight e^-80: valid only while their weight sums are
+            // moderate (their share of any denominator stays below 2^-53); otherwise log-domain kernel
+            bool ok = true;
+            for (int k = 0; k < K; ++k)
+                if (!(c->h_Nk[k] > 0)) {
+                    const double S = c->h_out[lay.S() + k];
+                    if (!(S > 1e-250 && S < 1e12)) ok = false;
+                    c->h_out[lay.logS() + k] = std::log(S);
+                    c->h_out[lay.S() + k] = 0.0;           // contract: S = 0 for unsampled states
+                }
+            if (!ok) continue;
+        }
         if (logAll) {
             for (int k : c->active) c->h_out[lay.S() + k] = std::exp(c->h_out[lay.logS() + k]);
             break;
@@ -566,7 +579,7 @@ int mbar_b200_sci_iterate(mbar_b200_ctx* c, double* f, int32_t iters) {
     const int K = c->K;
     FusedParams p;
     bool ok = false;
-    if (c->kernelChoice != MBAR_B200_KERNEL_GENERIC) MBAR_TRY(fused_prepare(c, f, false, &p, &ok));
+    if (c->kernelChoice != MBAR_B200_KERNEL_GENERIC) MBAR_TRY(fused_prepare(c, f, false, false, &p, &ok));
     if (!ok) {
         // host-stepped fallback with the generic kernel
         std::vector<double> cur(f, f + K);

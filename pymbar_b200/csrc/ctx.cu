@@ -66,11 +66,14 @@ __global__ void __launch_bounds__(256) retile_kernel(const double* __restrict__ 
     if (!valid || !finiteShift) x = 0.0;
 
     double* out = dst + (tile0 + tileLocal) * (int64_t)K * TILE_N + lane;
+    int extreme = 0;
     for (int k = warp; k < K; k += 8) {
         double v = valid ? colp[(int64_t)k * ld] : 0.0;
         v = fmin(v - x, U_CLAMP);
+        if (valid && v < -1.0e5) extreme = 4;   // only possible for unsampled rows (sampled rows are >= 0)
         out[(int64_t)k * TILE_N] = valid ? v : 0.0;
     }
+    if (__any_sync(0xffffffffu, extreme) && lane == 0) atomicOr(&flags[1], 1);
     if (warp == 0) xshift[(tile0 + tileLocal) * TILE_N + lane] = x;
     if (anyBad && threadIdx.x == 0) atomicOr(&flags[0], anyBad);
 }
@@ -295,6 +298,7 @@ int mbar_b200_create(mbar_b200_ctx** out, int device, int32_t K, int64_t N_local
     c->smCount = prop.multiProcessorCount;
     c->h_Nk.assign(N_k, N_k + K);
     c->h_logNk.resize(K);
+    c->h_logNkEff.resize(K);
     std::vector<unsigned long long> mask((K + 63) / 64, 0ull);
     for (int k = 0; k < K; ++k) {
         if (!(N_k[k] >= 0.0)) {
@@ -307,8 +311,10 @@ int mbar_b200_create(mbar_b200_ctx** out, int device, int32_t K, int64_t N_local
             c->active.push_back(k);
             mask[k >> 6] |= 1ull << (k & 63);
             c->h_logNk[k] = std::log(N_k[k]);
+            c->h_logNkEff[k] = c->h_logNk[k];
         } else {
             c->h_logNk[k] = -INFINITY;
+            c->h_logNkEff[k] = LOG_EPS_UNSAMPLED;
         }
     }
     if (c->active.empty()) {
@@ -334,6 +340,7 @@ int mbar_b200_create(mbar_b200_ctx** out, int device, int32_t K, int64_t N_local
     ALLOC(c->d_xshift, nPad * sizeof(double));
     ALLOC(c->d_c, 4 * (size_t)K * sizeof(double));
     ALLOC(c->d_Nk, (size_t)K * sizeof(double));
+    ALLOC(c->d_NkEff, (size_t)K * sizeof(double));
     ALLOC(c->d_rowmask, mask.size() * sizeof(unsigned long long));
     ALLOC(c->d_zeromask, mask.size() * sizeof(unsigned long long));
     ALLOC(c->d_onesmask, mask.size() * sizeof(unsigned long long));
@@ -353,6 +360,11 @@ int mbar_b200_create(mbar_b200_ctx** out, int device, int32_t K, int64_t N_local
     MBAR_CUDA(cudaEventCreateWithFlags(&c->evCopy[0], cudaEventDisableTiming));
     MBAR_CUDA(cudaEventCreateWithFlags(&c->evCopy[1], cudaEventDisableTiming));
     MBAR_CUDA(cudaMemcpy(c->d_Nk, N_k, (size_t)K * sizeof(double), cudaMemcpyHostToDevice));
+    {
+        std::vector<double> eff(K);
+        for (int k = 0; k < K; ++k) eff[k] = std::exp(c->h_logNkEff[k]);
+        MBAR_CUDA(cudaMemcpy(c->d_NkEff, eff.data(), (size_t)K * sizeof(double), cudaMemcpyHostToDevice));
+    }
     MBAR_CUDA(cudaMemcpy(c->d_rowmask, mask.data(), mask.size() * sizeof(unsigned long long),
                          cudaMemcpyHostToDevice));
     MBAR_CUDA(cudaMemset(c->d_zeromask, 0, mask.size() * sizeof(unsigned long long)));
@@ -370,7 +382,7 @@ int mbar_b200_destroy(mbar_b200_ctx* c) {
     for (void* pm : c->peerMapped) cudaIpcCloseMemHandle(pm);
     cudaFree(c->d_inbox);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_u); cudaFree(c->d_xshift); cudaFree(c->d_c); cudaFree(c->d_Nk);
+    cudaFree(c->d_u); cudaFree(c->d_xshift); cudaFree(c->d_c); cudaFree(c->d_Nk); cudaFree(c->d_NkEff);
     cudaFree(c->d_rowmask); cudaFree(c->d_zeromask); cudaFree(c->d_onesmask); cudaFree(c->d_partial); cudaFree(c->d_out); cudaFree(c->d_L);
     cudaFree(c->d_W); cudaFree(c->d_ticket); cudaFree(c->d_flag); cudaFree(c->d_f);
     cudaFree(c->d_scratch);
@@ -444,6 +456,8 @@ static int finish_upload(mbar_b200_ctx* c) {
     MBAR_CUDA(cudaStreamSynchronize(c->copyStream));
     MBAR_CUDA(cudaStreamSynchronize(c->stream));
     MBAR_CUDA(cudaMemcpy(flags, c->d_flag, sizeof(flags), cudaMemcpyDeviceToHost));
+    c->unsampledExtreme = flags[1] != 0;
+    if (flags[1]) MBAR_CUDA(cudaMemset(c->d_flag + 1, 0, sizeof(int)));
     if (flags[0]) {
         MBAR_CUDA(cudaMemset(c->d_flag, 0, 4 * sizeof(int)));
         c->ready = false;

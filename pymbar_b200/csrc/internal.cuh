@@ -17,6 +17,9 @@ constexpr double U_CLAMP = 1.0e6;       // shifted energies are clamped to [.., 
 constexpr double C_RANGE = 1.0e6;       // |f_k + log N_k| must stay below this
 constexpr double FUSED_SPREAD = 1200.0; // fused kernel needs max(c) - min(c) below this
 constexpr int MAX_GRID = 148 * 4;
+// Unsampled states ride through the fused kernel as "sampled with weight e^-80": their share of any
+// denominator is below 2^-53 as long as their sum of weights stays below 1e12 (checked by the host).
+constexpr double LOG_EPS_UNSAMPLED = -80.0;
 
 void set_error(const char* fmt, ...);
 #define MBAR_CUDA(call)                                                                     \
@@ -73,6 +76,9 @@ struct mbar_b200_ctx {
 
     std::vector<double> h_Nk;       // [K]
     std::vector<double> h_logNk;    // [K], -inf for unsampled
+    std::vector<double> h_logNkEff; // [K], LOG_EPS_UNSAMPLED for unsampled
+    double* d_NkEff = nullptr;      // [K], exp(LOG_EPS_UNSAMPLED) for unsampled
+    bool unsampledExtreme = false;  // an unsampled state lies > 1e5 kT below every sampled one somewhere
     std::vector<int> active;        // indices of sampled states
     int firstActive = 0;
     double N_total_states = 0;      // sum_k N_k (global N)
@@ -140,7 +146,7 @@ struct FusedParams {
     int epi, first;
     int64_t N, nTiles, nStages;
     double mid;
-    int K, Wk, Wn, Rw, TPW, NS, CW, batch, debugSkip, mode, CL, Kh;
+    int K, Wk, Wn, Rw, TPW, NS, CW, batch, debugSkip, mode, CL, Kh, allStates;
     uint32_t tileBytes, stageBytes;
 };
 
@@ -148,10 +154,10 @@ struct FusedParams {
 int retile_chunk(mbar_b200_ctx* ctx, const double* d_rowmajor, int64_t ldCols, int64_t tile0,
                  int64_t nTilesChunk, int64_t validCols, cudaStream_t s);
 int launch_pass_generic(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool logAll);
-int launch_pass_fused(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool* usedOut);
-int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams* out, bool* ok);
+int launch_pass_fused(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, bool* usedOut);
+int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, FusedParams* out, bool* ok);
 int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p);
-bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, double* midOut);
+bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, bool allStates, double* midOut, double* spreadOut);
 int launch_hessian(mbar_b200_ctx* ctx, const double* h_f, bool allRows);
 int launch_logw(mbar_b200_ctx* ctx, const double* h_f, double* logW_host, int64_t ld, int expo);
 int launch_synth(mbar_b200_ctx* ctx, const mbar_b200_synth* spec);

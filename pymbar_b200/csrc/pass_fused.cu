@@ -477,11 +477,14 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
     }
 }
 
-bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, double* midOut) {
+bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, bool allStates, double* midOut,
+                      double* spreadOut) {
     if (ctx->K > 512) return false;
+    if (allStates && ctx->unsampledExtreme) return false;
     double lo = INFINITY, hi = -INFINITY;
-    for (int k : ctx->active) {
-        const double c = h_f[k] + ctx->h_logNk[k];
+    for (int k = 0; k < ctx->K; ++k) {
+        if (!allStates && !(ctx->h_Nk[k] > 0)) continue;
+        const double c = h_f[k] + ctx->h_logNkEff[k];
         if (!std::isfinite(c)) return false;
         lo = std::fmin(lo, c);
         hi = std::fmax(hi, c);
@@ -489,14 +492,16 @@ bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, double* midOu
     if (hi - lo >= FUSED_SPREAD) return false;
     if (std::fabs(hi) > C_RANGE || std::fabs(lo) > C_RANGE) return false;
     if (midOut) *midOut = 0.5 * (hi + lo);
+    if (spreadOut) *spreadOut = hi - lo;
     return true;
 }
 
 // Configure the fused kernel for f (host) and stage c = f + log N - mid on the device.
-int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams* out, bool* ok) {
+int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, FusedParams* out,
+                  bool* ok) {
     *ok = false;
-    double mid = 0.0;
-    if (!fused_applicable(ctx, h_f, &mid)) return MBAR_B200_OK;
+    double mid = 0.0, spread = 0.0;
+    if (!fused_applicable(ctx, h_f, allStates, &mid, &spread)) return MBAR_B200_OK;
     const int K = ctx->K;
     FusedParams p{};
     p.K = K;
@@ -505,15 +510,8 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams
     int mode = 3;
     if (const char* v = std::getenv("MBAR_B200_FUSED_MODE")) mode = std::atoi(v) & 3;
     mode |= 1;   // the shuffle-gathered table (bit 0 clear) was measured 10 % slower and is retired
-    {
-        double lo = INFINITY, hi = -INFINITY;
-        for (int k : ctx->active) {
-            const double c = h_f[k] + ctx->h_logNk[k];
-            lo = std::fmin(lo, c);
-            hi = std::fmax(hi, c);
-        }
-        if (hi - lo > 600.0) mode &= 1;   // exp(c_k) * exp(-u') needs the spread inside the exponent range
-    }
+    if (spread > 600.0) mode &= 1;   // exp(c_k) * exp(-u') needs the spread inside the exponent range
+    p.allStates = allStates ? 1 : 0;
     const int cw = 8;
     const int rmax = 32;
     p.CL = K > 256 ? 2 : 1;                  // 256 < K <= 512: two-CTA clusters, half the states each
@@ -544,8 +542,9 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams
     p.mid = mid;
     p.u = ctx->d_u;
     p.c = ctx->d_c;
-    p.rowmask = ctx->d_rowmask;
-    p.Nk = ctx->d_Nk;
+    // allStates: unsampled rows take part with weight e^-80 (see LOG_EPS_UNSAMPLED)
+    p.rowmask = allStates ? ctx->d_onesmask : ctx->d_rowmask;
+    p.Nk = allStates ? ctx->d_NkEff : ctx->d_Nk;
     p.partial = ctx->d_partial;
     p.out = ctx->d_out;
     p.ticket = ctx->d_ticket;
@@ -553,7 +552,7 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, FusedParams
         MBAR_CUDA(cudaMalloc((void**)&ctx->d_L, (size_t)ctx->nTiles * TILE_N * sizeof(double)));
     p.Lout = wantL ? ctx->d_L : nullptr;
     for (int k = 0; k < K; ++k)
-        ctx->h_f[k] = std::isinf(ctx->h_logNk[k]) ? 0.0 : h_f[k] + ctx->h_logNk[k] - mid;
+        ctx->h_f[k] = (!allStates && std::isinf(ctx->h_logNk[k])) ? 0.0 : h_f[k] + ctx->h_logNkEff[k] - mid;
     MBAR_CUDA(cudaMemcpyAsync(ctx->d_c, ctx->h_f, (size_t)K * sizeof(double), cudaMemcpyHostToDevice,
                               ctx->stream));
     ctx->h2dBytes += K * 8;
@@ -568,7 +567,7 @@ int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
     int64_t grid = p.nStages < ctx->smCount / p.CL ? p.nStages : ctx->smCount / p.CL;
     grid *= p.CL;
     const int Rt = p.Rw <= 8 ? 8 : p.Rw <= 16 ? 16 : 32;
-    const bool full = (p.Rw == Rt) && (p.K == p.CL * p.Wk * p.Rw) && ((int)ctx->active.size() == p.K);
+    const bool full = (p.Rw == Rt) && (p.K == p.CL * p.Wk * p.Rw) && ((int)ctx->active.size() == p.K || p.allStates);
     void (*kern)(const FusedParams) = nullptr;
     int which = 0;
 #define PICK(R_, CL_, ID_)                                                                           \
@@ -612,9 +611,9 @@ int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
     return MBAR_B200_OK;
 }
 
-int launch_pass_fused(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool* usedOut) {
+int launch_pass_fused(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, bool* usedOut) {
     FusedParams p;
-    MBAR_TRY(fused_prepare(ctx, h_f, wantL, &p, usedOut));
+    MBAR_TRY(fused_prepare(ctx, h_f, wantL, allStates, &p, usedOut));
     if (!*usedOut) return MBAR_B200_OK;
     return fused_enqueue(ctx, p);
 }
