@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-fPIC", "-ldl"]
+           "-Xcompiler", "-fPIC", "-ldl", "-lpthread"]
     subprocess.check_call(cmd)
     return LIB
 

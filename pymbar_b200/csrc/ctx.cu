@@ -10,7 +10,8 @@
 // objective changes by the constant sum_n x_n which the context carries.
 #include <cmath>
 #include <cstring>
-#include <mutex>
+#include <algorithm>
+#include <thread>
 
 #include "internal.cuh"
 
@@ -495,9 +496,21 @@ int mbar_b200_upload_u_kn(mbar_b200_ctx* c, const double* u_host, int64_t ld) {
         if (!pinned) {
             // pageable memory: pack the chunk into the pinned staging buffer on the CPU
             MBAR_CUDA(cudaEventSynchronize(c->evCopy[buf]));
+            // (numpy arrays are pageable: pack with several threads so the packing keeps up with PCIe)
             double* p = c->stage_pinned[buf];
-            for (int k = 0; k < K; ++k)
-                std::memcpy(p + (size_t)k * w, u_host + (size_t)k * ld + n0, (size_t)w * sizeof(double));
+            const int nthr = std::max(1, std::min({8, K, (int)std::thread::hardware_concurrency()}));
+            auto pack = [&](int t) {
+                for (int k = t; k < K; k += nthr)
+                    std::memcpy(p + (size_t)k * w, u_host + (size_t)k * ld + n0, (size_t)w * sizeof(double));
+            };
+            if (nthr == 1 || (size_t)w * K < (1u << 16)) {
+                for (int t = 0; t < nthr; ++t) pack(t);
+            } else {
+                std::vector<std::thread> th;
+                for (int t = 1; t < nthr; ++t) th.emplace_back(pack, t);
+                pack(0);
+                for (auto& x : th) x.join();
+            }
             src = p;
             srcLd = w;
         }
