@@ -33,3 +33,34 @@ def ensure_type(val, dtype, ndim, name, shape=None, warn_on_cast=True):
         if len(shape) != val.ndim or any(s is not None and s != t for s, t in zip(shape, val.shape)):
             raise ValueError(f"{name} must be shape {tuple(shape)}. You supplied  {val.shape}")
     return val
+
+
+def kln_to_kn(kln, N_k=None, cleanup=False):
+    """Vectorised pymbar.utils.kln_to_kn (utils.py:41-75): [K, L, N_max] -> [L, N] in block order.
+
+    The reference copies one column per Python iteration (N iterations); this copies one state block
+    per iteration (K iterations), which matters once the solve itself takes milliseconds
+    (SURVEY.md 8f, row N4).  Same semantics, including N_k = None meaning N_max samples per state."""
+    kln = np.asarray(kln)
+    K, L, N_max = kln.shape
+    if N_k is None:
+        N_k = N_max * np.ones([L], dtype=np.int64)
+    N_k = np.asarray(N_k, dtype=np.int64)
+    N = int(np.sum(N_k[:K]))
+    kn = np.zeros([L, N], dtype=np.float64)
+    i = 0
+    for k in range(K):
+        n = int(N_k[k])
+        kn[:, i:i + n] = kln[k, :, :n]
+        i += n
+    return kn
+
+
+def kn_to_n(kn, N_k=None, cleanup=False):
+    """Vectorised pymbar.utils.kn_to_n (utils.py:78-114): [K, N_max] -> [N] in block order."""
+    kn = np.asarray(kn)
+    K, N_max = kn.shape
+    if N_k is None:
+        N_k = N_max * np.ones([K], dtype=np.int64)
+    N_k = np.asarray(N_k, dtype=np.int64)
+    return np.concatenate([kn[k, :int(N_k[k])] for k in range(K)]).astype(np.float64) if K else np.zeros(0)
