@@ -109,6 +109,11 @@ int mbar_b200_upload_u_kn(mbar_b200_ctx* ctx, const double* u_host, int64_t ld);
 int mbar_b200_upload_u_kn_dev(mbar_b200_ctx* ctx, const double* u_dev, int64_t ld);
 /* Fill the context on device from the synthetic family (no host traffic). */
 int mbar_b200_synthesize(mbar_b200_ctx* ctx, const mbar_b200_synth* spec);
+/* Per-sample multiplicities w_n >= 0 ([N_local] host doubles; NULL restores w_n = 1).  Every sum over
+ * samples becomes a weighted sum (S_k = sum_n w_n W_nk, sum_n w_n L_n, W^T diag(w) W) while the denominators
+ * L_n are untouched: a bootstrap replicate of mbar.py:417-449 (`u_kn[:, rints]`, an 8*K*N gather per
+ * replicate) is the same data with w_n = number of times sample n was drawn — no copy, same kernels. */
+int mbar_b200_set_sample_weights(mbar_b200_ctx* ctx, const double* w_host);
 /* Read back columns [n0, n0+n) of the ORIGINAL (unshifted) u_kn as [K, n] row-major, stride ld. */
 int mbar_b200_download_u_kn(mbar_b200_ctx* ctx, int64_t n0, int64_t n, double* u_host, int64_t ld);
 

@@ -111,6 +111,12 @@ def case(name, u_kn, N_k, store_u, regen, rng):
         data["est_N_eff"] = np.array(m.compute_effective_sample_number())
         W = np.exp(m.Log_W_nk)
         data["est_G"] = W.T @ W
+    if store_u:
+        # bootstrap replicates (mbar.py:417-449) with a fixed rseed: indices and the re-solved f_k
+        mb = pymbar.MBAR(u_kn, N_k, n_bootstraps=4, rseed=11)
+        data["boot_rints"] = np.array(mb.bootstrap_rints)
+        data["boot_f_k"] = np.array(mb.f_k_boots)
+        data["boot_f_k_start"] = np.array(mb.f_k)
     # adaptive trajectory from f=0 on sampled states (mbar_solvers.py:510-667), tol 1e-12
     sampled = N_k > 0
     us = ref.precondition_u_kn(u_kn[sampled], 1.0 * N_k[sampled], np.zeros(sampled.sum()))

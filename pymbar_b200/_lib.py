@@ -53,6 +53,7 @@ SIGNATURES = {
     "mbar_b200_upload_u_kn": (C.c_int, [_ctx, C.c_void_p, C.c_int64]),
     "mbar_b200_upload_u_kn_dev": (C.c_int, [_ctx, C.c_void_p, C.c_int64]),
     "mbar_b200_synthesize": (C.c_int, [_ctx, C.POINTER(Synth)]),
+    "mbar_b200_set_sample_weights": (C.c_int, [_ctx, C.c_void_p]),
     "mbar_b200_download_u_kn": (C.c_int, [_ctx, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),
     "mbar_b200_pass": (C.c_int, [_ctx, _dp, _dp, _dp, _dp]),
     "mbar_b200_self_consistent_update": (C.c_int, [_ctx, _dp, _dp]),

@@ -203,9 +203,10 @@ static int run_pass(mbar_b200_ctx* c, const double* f, PassWant want) {
 
 static double global_sumx(mbar_b200_ctx* c, int* rc) {
     *rc = MBAR_B200_OK;
-    if (!c->comm || c->nranks == 1) return c->sumX;
+    const double mine = c->d_wgt ? c->sumXw : c->sumX;
+    if (!c->comm || c->nranks == 1) return mine;
     double* d = c->d_scratch;
-    cudaMemcpyAsync(d, &c->sumX, sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(d, &mine, sizeof(double), cudaMemcpyHostToDevice, c->stream);
     *rc = comm_allreduce(c, d, 1, 0);
     double v = 0.0;
     cudaMemcpyAsync(&v, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream);

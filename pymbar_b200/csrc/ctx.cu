@@ -132,6 +132,64 @@ __global__ void __launch_bounds__(256) sumx_kernel(const double* __restrict__ x,
     }
 }
 
+// sqrt(w_n) and the partial sums of w_n x_n (weighted counterpart of sumx_kernel)
+__global__ void __launch_bounds__(256) wprep_kernel(const double* __restrict__ w, const double* __restrict__ x,
+                                                    int64_t N, double* __restrict__ sqrtw,
+                                                    double* __restrict__ partial) {
+    __shared__ double s[8];
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double wi = w[i];
+        sqrtw[i] = sqrt(wi);
+        acc += wi * x[i];
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += s[i];
+        partial[blockIdx.x] = t;
+    }
+}
+
+int set_weights(mbar_b200_ctx* ctx, const double* w_host) {
+    if (!w_host) {
+        cudaFree(ctx->d_wgt);
+        cudaFree(ctx->d_sqrtw);
+        ctx->d_wgt = ctx->d_sqrtw = nullptr;
+        return MBAR_B200_OK;
+    }
+    const size_t nPad = (size_t)ctx->nTiles * TILE_N;
+    if (!ctx->d_wgt) {
+        MBAR_CUDA(cudaMalloc((void**)&ctx->d_wgt, nPad * sizeof(double)));
+        MBAR_CUDA(cudaMalloc((void**)&ctx->d_sqrtw, nPad * sizeof(double)));
+    }
+    double sw = 0.0;
+    for (int64_t i = 0; i < ctx->N; ++i) {
+        MBAR_REQUIRE(w_host[i] >= 0.0, MBAR_B200_ERR_INVALID, "sample weight %lld is negative or NaN", (long long)i);
+        sw += w_host[i];
+    }
+    ctx->sumW = sw;
+    MBAR_CUDA(cudaMemsetAsync(ctx->d_wgt, 0, nPad * sizeof(double), ctx->stream));
+    MBAR_CUDA(cudaMemsetAsync(ctx->d_sqrtw, 0, nPad * sizeof(double), ctx->stream));
+    MBAR_CUDA(cudaMemcpyAsync(ctx->d_wgt, w_host, (size_t)ctx->N * sizeof(double), cudaMemcpyHostToDevice,
+                              ctx->stream));
+    ctx->h2dBytes += ctx->N * 8;
+    const int grid = 256;
+    wprep_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_wgt, ctx->d_xshift, ctx->N, ctx->d_sqrtw, ctx->d_scratch);
+    ctx->launches++;
+    MBAR_CUDA(cudaGetLastError());
+    std::vector<double> h(grid);
+    MBAR_CUDA(cudaMemcpyAsync(h.data(), ctx->d_scratch, grid * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MBAR_CUDA(cudaStreamSynchronize(ctx->stream));
+    double t = 0.0;
+    for (double v : h) t += v;
+    ctx->sumXw = t;
+    return MBAR_B200_OK;
+}
+
 int reduce_sumx(mbar_b200_ctx* ctx) {
     const int grid = 256;
     sumx_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_xshift, ctx->N, ctx->d_scratch);
@@ -383,7 +441,7 @@ int mbar_b200_destroy(mbar_b200_ctx* c) {
     for (void* pm : c->peerMapped) cudaIpcCloseMemHandle(pm);
     cudaFree(c->d_inbox);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_u); cudaFree(c->d_xshift); cudaFree(c->d_c); cudaFree(c->d_Nk); cudaFree(c->d_NkEff);
+    cudaFree(c->d_u); cudaFree(c->d_xshift); cudaFree(c->d_wgt); cudaFree(c->d_sqrtw); cudaFree(c->d_c); cudaFree(c->d_Nk); cudaFree(c->d_NkEff);
     cudaFree(c->d_rowmask); cudaFree(c->d_zeromask); cudaFree(c->d_onesmask); cudaFree(c->d_partial); cudaFree(c->d_out); cudaFree(c->d_L);
     cudaFree(c->d_W); cudaFree(c->d_ticket); cudaFree(c->d_flag); cudaFree(c->d_f);
     cudaFree(c->d_scratch);
@@ -545,6 +603,13 @@ int mbar_b200_synthesize(mbar_b200_ctx* c, const mbar_b200_synth* spec) {
     MBAR_TRY(reduce_sumx(c));
     c->ready = true;
     return MBAR_B200_OK;
+}
+
+int mbar_b200_set_sample_weights(mbar_b200_ctx* c, const double* w_host) {
+    MBAR_REQUIRE(c, MBAR_B200_ERR_INVALID, "ctx is NULL");
+    MBAR_REQUIRE(c->ready, MBAR_B200_ERR_NOT_READY, "u_kn not uploaded");
+    MBAR_CUDA(cudaSetDevice(c->device));
+    return set_weights(c, w_host);
 }
 
 int mbar_b200_download_u_kn(mbar_b200_ctx* c, int64_t n0, int64_t n, double* u_host, int64_t ld) {

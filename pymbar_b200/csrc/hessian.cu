@@ -34,11 +34,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 // Converts row `row` of a 128 x 32 energy panel into weights in place (swizzled store).
 __device__ __forceinline__ void convert_row(double* P, int row, int lane, double ck, bool act, bool valid,
-                                            double L, const double* tab) {
+                                            double L, const double* tab, double sw) {
     const double v = P[row * TILE_N + lane];
     __syncwarp();   // every lane has read the row before any lane overwrites a permuted slot of it
     double wv = 0.0;
-    if (valid && act) wv = exp_fast(fmin(fmax(ck - v - L, -800.0), 700.0), tab);
+    if (valid && act) wv = sw * exp_fast(fmin(fmax(ck - v - L, -800.0), 700.0), tab);
     P[row * TILE_N + (lane ^ ((row & 7) << 2))] = wv;
 }
 
@@ -53,7 +53,8 @@ struct HessSplit {
 __global__ void __launch_bounds__(512, 1)
 hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
                const double* __restrict__ c, const unsigned long long* __restrict__ rowmask, int K,
-               int64_t N, int64_t nTiles, const HessSplit split, double* __restrict__ Gpart) {
+               int64_t N, int64_t nTiles, const HessSplit split, double* __restrict__ Gpart,
+               const double* __restrict__ sqrtw) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* tab = reinterpret_cast<double*>(smem_raw);                      // [32]
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(tab + 32);             // [HNS]
@@ -137,14 +138,15 @@ hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
     // prologue: weights of the first tile
     if (nIter > 0) {
         const double L = Lp[t0 * TILE_N + lane];
+        const double sw0 = sqrtw ? sqrtw[t0 * TILE_N + lane] : 1.0;   // sqrt of the bootstrap multiplicity
         const bool valid = t0 * TILE_N + lane < N;
         mbar_wait(smem_u32(&bar_full[0]), 0);
         double* Pi = reinterpret_cast<double*>(ring);
         double* Pj = Pi + HB * TILE_N;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            convert_row(Pi, warp * 8 + r, lane, cI[r], (actI >> r) & 1u, valid, L, tab);
-            if (!diag) convert_row(Pj, warp * 8 + r, lane, cJ[r], (actJ >> r) & 1u, valid, L, tab);
+            convert_row(Pi, warp * 8 + r, lane, cI[r], (actI >> r) & 1u, valid, L, tab, sw0);
+            if (!diag) convert_row(Pj, warp * 8 + r, lane, cJ[r], (actJ >> r) & 1u, valid, L, tab, sw0);
         }
     }
     __syncthreads();
@@ -156,10 +158,11 @@ hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
         // the NEXT tile's energies are converted while this tile is multiplied (separate pipes)
         const bool haveNext = it + 1 < nIter;
         const int nslot = (it + 1) % HNS;
-        double Ln = 0.0;
+        double Ln = 0.0, swn = 1.0;
         bool validN = false;
         if (haveNext) {
             Ln = Lp[(tile + 1) * TILE_N + lane];
+            if (sqrtw) swn = sqrtw[(tile + 1) * TILE_N + lane];
             validN = (tile + 1) * TILE_N + lane < N;
             mbar_wait(smem_u32(&bar_full[nslot]), ((it + 1) / HNS) & 1);
         }
@@ -172,8 +175,8 @@ hessian_kernel(const double* __restrict__ u, const double* __restrict__ Lp,
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
             if (haveNext) {
-                convert_row(Ni, warp * 8 + ks, lane, cI[ks], (actI >> ks) & 1u, validN, Ln, tab);
-                if (!diag) convert_row(Nj, warp * 8 + ks, lane, cJ[ks], (actJ >> ks) & 1u, validN, Ln, tab);
+                convert_row(Ni, warp * 8 + ks, lane, cI[ks], (actI >> ks) & 1u, validN, Ln, tab, swn);
+                if (!diag) convert_row(Nj, warp * 8 + ks, lane, cJ[ks], (actJ >> ks) & 1u, validN, Ln, tab, swn);
             }
             if (!mmaWarp) continue;
             const int col = ((ks ^ fragRow) << 2) + fragCol;      // (4 ks + fragCol) ^ (fragRow << 2)
@@ -274,7 +277,7 @@ int launch_hessian(mbar_b200_ctx* ctx, const double* h_f, bool allRows) {
     const PassLayout lay{K};
     hessian_kernel<<<nCtas, 512, smem, ctx->stream>>>(
         ctx->d_u, ctx->d_L, ctx->d_c + 2 * K, allRows ? ctx->d_onesmask : ctx->d_rowmask, K, ctx->N, ctx->nTiles,
-        split, ctx->d_W);
+        split, ctx->d_W, ctx->d_sqrtw);
     MBAR_CUDA(cudaGetLastError());
     hessian_reduce_kernel<<<dim3(nPairs, 16), 256, 0, ctx->stream>>>(ctx->d_W, K, split, ctx->d_out + lay.G());
     MBAR_CUDA(cudaGetLastError());

@@ -85,6 +85,10 @@ struct mbar_b200_ctx {
 
     double* d_u = nullptr;          // [nTiles][K][32] shifted, clamped
     double* d_xshift = nullptr;     // [nTiles*32] per-sample shift x_n = min over sampled k of u_kn
+    double* d_wgt = nullptr;        // [nTiles*32] per-sample multiplicities w_n (bootstrap), or NULL = all 1
+    double* d_sqrtw = nullptr;      // [nTiles*32] sqrt(w_n) for the second-moment kernel
+    double sumW = 0.0;              // sum_n w_n over valid local samples (= N when unweighted)
+    double sumXw = 0.0;             // sum_n w_n x_n
     double sumX = 0.0;              // sum_n x_n over valid local samples
     double* d_c = nullptr;          // [2][K] c_k = f_k + log N_k - mid (fused) | f_k (row K..2K)
     double* d_Nk = nullptr;         // [K]
@@ -139,6 +143,8 @@ struct FusedParams {
     double* out;
     unsigned int* ticket;
     double* Lout;                          // [nTiles*32] shifted-frame L'_n, or NULL
+    const double* wgt;                     // [nTiles*32] sample multiplicities or NULL
+    double sumW;                           // sum of the multiplicities of this shard (N if unweighted)
     double* f;                             // [K] device f_k (epilogue) or NULL
     double* cnext;                         // [K] where the epilogue writes c for the next launch
     PeerCfg peer;
@@ -164,6 +170,7 @@ int launch_synth(mbar_b200_ctx* ctx, const mbar_b200_synth* spec);
 int launch_untile(mbar_b200_ctx* ctx, int64_t n0, int64_t n, double* d_dst, int64_t ld);
 int comm_allreduce(mbar_b200_ctx* ctx, double* d_buf, int count, int op /*0 sum, 2 max*/);
 int reduce_sumx(mbar_b200_ctx* ctx);
+int set_weights(mbar_b200_ctx* ctx, const double* w_host);
 
 // ---- device helpers ----
 #ifdef __CUDACC__

@@ -299,6 +299,8 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                 const int64_t tile = s * tilesPerStage + tis;
                 if (tile >= p.nTiles) break;   // uniform over the sample group
                 const double* tp = sb + ((size_t)tis * Kl + k0) * TILE_N + lane;
+                // bootstrap multiplicity of this lane's sample (issued early; used after the exps)
+                const double wn = p.wgt ? __ldg(p.wgt + tile * TILE_N + lane) : 1.0;
                 double e[R];
                 double Dp = 0.0;
                 {
@@ -336,13 +338,17 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                 }
                 const bool valid = tile * TILE_N + lane < p.N;
                 if (valid && !(D > 1e-250 && D < 1e250)) bad = 1;
-                const double invD = valid ? 1.0 / D : 0.0;
+                const double invD = valid ? wn / D : 0.0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) acc[r] = fma(e[r], invD, acc[r]);
                 if (w == 0 && half == 0) {
                     if (valid) {
-                        logprod_push(D, mprod, esum);
-                        if ((++npush & 255) == 0) logprod_renorm(mprod, esum);
+                        if (p.wgt) {
+                            sumL += wn * log(D);          // general multiplicities: one log per sample
+                        } else {
+                            logprod_push(D, mprod, esum);
+                            if ((++npush & 255) == 0) logprod_renorm(mprod, esum);
+                        }
                     }
                     if (p.Lout) p.Lout[tile * TILE_N + lane] = log(D) + p.mid;
                 }
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
             const double t = warp_sum(acc[r]);
             if (lane == 0 && r < p.Rw && k0 + r < Kl) sred[g * Kl + k0 + r] = t;
         }
-        sumL = (double)esum * 0.693147180559945309417232 + log(mprod);
+        sumL += (double)esum * 0.693147180559945309417232 + log(mprod);
         sumL = warp_sum(sumL);
         bad = __any_sync(0xffffffffu, bad);
         if (lane == 0) {
@@ -400,7 +406,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
     for (int k = threadIdx.x; k < K + 2; k += blockDim.x) {
         double t = 0.0;
         for (unsigned b = 0; b < nGroups; ++b) t += p.partial[(size_t)b * (K + 2) + k];
-        if (k == K) t += (double)p.N * p.mid;
+        if (k == K) t += p.sumW * p.mid;
         tot[k] = t;
     }
     __syncthreads();
@@ -551,6 +557,8 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allSta
     if (wantL && !ctx->d_L)
         MBAR_CUDA(cudaMalloc((void**)&ctx->d_L, (size_t)ctx->nTiles * TILE_N * sizeof(double)));
     p.Lout = wantL ? ctx->d_L : nullptr;
+    p.wgt = ctx->d_wgt;
+    p.sumW = ctx->d_wgt ? ctx->sumW : (double)ctx->N;
     for (int k = 0; k < K; ++k)
         ctx->h_f[k] = (!allStates && std::isinf(ctx->h_logNk[k])) ? 0.0 : h_f[k] + ctx->h_logNkEff[k] - mid;
     MBAR_CUDA(cudaMemcpyAsync(ctx->d_c, ctx->h_f, (size_t)K * sizeof(double), cudaMemcpyHostToDevice,

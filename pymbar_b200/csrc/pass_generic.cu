@@ -28,7 +28,7 @@ pass_generic_kernel(const double* __restrict__ u, int K, int64_t N, int64_t nTil
                     const unsigned long long* __restrict__ linmask,
                     const double* __restrict__ Nk, double* __restrict__ partial,
                     double* __restrict__ out, unsigned int* __restrict__ ticket,
-                    double* __restrict__ Lout, int warpsPerCta) {
+                    double* __restrict__ Lout, const double* __restrict__ wgt, int warpsPerCta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* tab = reinterpret_cast<double*>(smem_raw);                 // [32]
     double* trans = tab + 32;                                          // [W][32*33]
@@ -53,6 +53,8 @@ pass_generic_kernel(const double* __restrict__ u, int K, int64_t N, int64_t nTil
     for (int64_t tile = (int64_t)blockIdx.x * W + warp; tile < nTiles; tile += (int64_t)gridDim.x * W) {
         const double* tp = u + tile * (int64_t)K * TILE_N + lane;
         const bool valid = tile * TILE_N + lane < N;
+        const double wn = wgt ? __ldg(wgt + tile * TILE_N + lane) : 1.0;   // bootstrap multiplicity
+        const double logwn = wgt ? log(wn) : 0.0;
         double m = -INFINITY;
         for (int k = 0; k < K; ++k)
             if (row_active(rowmask, k)) m = fmax(m, __ldg(c + k) - tp[(int64_t)k * TILE_N]);
@@ -62,7 +64,7 @@ pass_generic_kernel(const double* __restrict__ u, int K, int64_t N, int64_t nTil
                 D += exp_fast(fmax(__ldg(c + k) - tp[(int64_t)k * TILE_N] - m, -800.0), tab);
         const double Lp = m + log(D);
         if (Lout) Lout[tile * TILE_N + lane] = Lp;
-        if (valid) sumL += Lp;
+        if (valid) sumL += wn * Lp;
         for (int k0 = 0; k0 < K; k0 += 32) {
             const int kmax = min(32, K - k0);
             for (int kk = 0; kk < kmax; ++kk) {
@@ -70,9 +72,9 @@ pass_generic_kernel(const double* __restrict__ u, int K, int64_t N, int64_t nTil
                 const double uv = tp[(int64_t)k * TILE_N];
                 double val;
                 if (row_active(linmask, k))
-                    val = valid ? exp_fast(fmax(__ldg(c + k) - uv - Lp, -800.0), tab) : 0.0;
+                    val = valid ? wn * exp_fast(fmax(__ldg(c + k) - uv - Lp, -800.0), tab) : 0.0;
                 else
-                    val = (kNeedUnsampled && valid) ? (__ldg(f + k) - uv - Lp) : -INFINITY;
+                    val = (kNeedUnsampled && valid) ? (__ldg(f + k) - uv - Lp + logwn) : -INFINITY;
                 T[kk * 33 + lane] = val;
             }
             __syncwarp();
@@ -214,7 +216,7 @@ int launch_pass_generic(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool 
                                                        ctx->d_c + K, ctx->d_rowmask,
                                                        logAll ? ctx->d_zeromask : ctx->d_rowmask, ctx->d_Nk,
                                                        ctx->d_partial, ctx->d_out, ctx->d_ticket,
-                                                       wantL ? ctx->d_L : nullptr, W);
+                                                       wantL ? ctx->d_L : nullptr, ctx->d_wgt, W);
     MBAR_CUDA(cudaEventRecord(ctx->evB, ctx->stream));
     ctx->launches++;
     ctx->passes++;

@@ -116,6 +116,16 @@ class DeviceProblem:
                           _dptr(O_k), _dptr(k_k))
         check(self._lib.mbar_b200_synthesize(self._h, C.byref(spec)))
 
+    def set_sample_weights(self, w):
+        """Per-sample multiplicities (bootstrap replicate without copying u_kn); None restores w = 1."""
+        if w is None:
+            check(self._lib.mbar_b200_set_sample_weights(self._h, None))
+            return
+        w = _f64(w)
+        if w.shape != (self.N,):
+            raise ValueError(f"weights must have shape ({self.N},)")
+        check(self._lib.mbar_b200_set_sample_weights(self._h, C.c_void_p(w.ctypes.data)))
+
     def download(self, n0=0, n=None, out=None):
         n = self.N - n0 if n is None else n
         if out is None:
