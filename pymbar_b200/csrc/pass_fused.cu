@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                 }
                 const bool valid = tile * TILE_N + lane < p.N;
                 if (valid && !(D > 1e-250 && D < 1e250)) bad = 1;
-                const double invD = valid ? wn / D : 0.0;
+                const double invD = valid ? (1.0 / D) * wn : 0.0;   // reciprocal (cheap) times multiplicity
 #pragma unroll
                 for (int r = 0; r < R; ++r) acc[r] = fma(e[r], invD, acc[r]);
                 if (w == 0 && half == 0) {
