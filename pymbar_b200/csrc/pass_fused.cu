@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                 if (tile >= p.nTiles) break;   // uniform over the sample group
                 const double* tp = sb + ((size_t)tis * Kl + k0) * TILE_N + lane;
                 // bootstrap multiplicity of this lane's sample (issued early; used after the exps)
-                const double wn = p.wgt ? __ldg(p.wgt + tile * TILE_N + lane) : 1.0;
+                // (only the masked kernel family carries the weighted path: the FULL family stays lean)
+                const double wn = (!FULL && p.wgt) ? __ldg(p.wgt + tile * TILE_N + lane) : 1.0;
                 double e[R];
                 double Dp = 0.0;
                 {
@@ -338,12 +339,12 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                 }
                 const bool valid = tile * TILE_N + lane < p.N;
                 if (valid && !(D > 1e-250 && D < 1e250)) bad = 1;
-                const double invD = valid ? (1.0 / D) * wn : 0.0;   // reciprocal (cheap) times multiplicity
+                const double invD = valid ? (FULL ? 1.0 / D : (1.0 / D) * wn) : 0.0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) acc[r] = fma(e[r], invD, acc[r]);
                 if (w == 0 && half == 0) {
                     if (valid) {
-                        if (p.wgt) {
+                        if (!FULL && p.wgt) {
                             sumL += wn * log(D);          // general multiplicities: one log per sample
                         } else {
                             logprod_push(D, mprod, esum);
@@ -575,7 +576,8 @@ int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
     int64_t grid = p.nStages < ctx->smCount / p.CL ? p.nStages : ctx->smCount / p.CL;
     grid *= p.CL;
     const int Rt = p.Rw <= 8 ? 8 : p.Rw <= 16 ? 16 : 32;
-    const bool full = (p.Rw == Rt) && (p.K == p.CL * p.Wk * p.Rw) && ((int)ctx->active.size() == p.K || p.allStates);
+    const bool full = (p.Rw == Rt) && (p.K == p.CL * p.Wk * p.Rw) &&
+                      ((int)ctx->active.size() == p.K || p.allStates) && !p.wgt;
     void (*kern)(const FusedParams) = nullptr;
     int which = 0;
 #define PICK(R_, CL_, ID_)                                                                           \

@@ -248,3 +248,44 @@ def test_tiny_and_ragged_shapes(lib, K, N_k):
     got = lib.mbar_solvers.solve_mbar_for_all_states(u, N_k, np.zeros(K), sws, proto)
     want = orc.solve_mbar_for_all_states(u, N_k, np.zeros(K), sws, orc.DEFAULT_SOLVER_PROTOCOL)
     np.testing.assert_allclose(got, want, atol=1e-8)
+
+
+def test_cluster_kernel_with_unsampled_states(lib):
+    """K > 256 (two-CTA clusters) together with empty states (weight e^-80 ride-along) and ragged N."""
+    from oracle import testsystems as ots
+
+    K = 300
+    N_k = np.full(K, 7)
+    N_k[[0, 17, 150, 299]] = 0
+    O, kk = np.linspace(1, 5, K), np.linspace(1, 3, K)
+    _, u, _ = ots.harmonic_u_kn(O, kk, N_k, seed=5)
+    Nf = N_k.astype(float)
+    f = np.random.RandomState(1).normal(scale=0.3, size=K)
+    with lib.DeviceProblem(u, Nf) as p:
+        for kern in ("auto", "generic"):
+            p.set_kernel(kern)
+            np.testing.assert_allclose(p.self_consistent_update(f), orc.self_consistent_update(u, Nf, f), atol=1e-10)
+        p.set_kernel("auto")
+        S, G = p.weight_moments(f)
+        W = orc.mbar_W_nk(u, Nf, f)
+        np.testing.assert_allclose(S, W.sum(0), rtol=1e-10)
+        np.testing.assert_allclose(G, W.T @ W, rtol=1e-9, atol=1e-14)
+
+
+def test_one_shot_host_entry(lib):
+    """mbar_b200_self_consistent_update_host: create + upload + pass + destroy in one C call."""
+    import ctypes as C
+
+    from pymbar_b200 import _lib
+
+    z = _cases.load("small_empty_state")
+    u = np.ascontiguousarray(z["u_kn"])
+    N = z["N_k"].astype(float)
+    f = z["f_rand"].copy()
+    out = np.empty_like(f)
+    dp = C.POINTER(C.c_double)
+    rc = _lib.load().mbar_b200_self_consistent_update_host(0, u.shape[0], u.shape[1], C.c_void_p(u.ctypes.data),
+                                                           u.shape[1], N.ctypes.data_as(dp), f.ctypes.data_as(dp),
+                                                           out.ctypes.data_as(dp))
+    assert rc == 0
+    np.testing.assert_allclose(out, z["rand_sci"], atol=1e-10)
