@@ -88,6 +88,10 @@ int mbar_b200_device_count(int* count);
 int mbar_b200_host_alloc(void** ptr, uint64_t bytes);
 int mbar_b200_host_free(void* ptr);
 
+/* Release the buffers parked by destroyed contexts (at most one u_kn-sized device buffer and one staging set
+ * per device are kept for the next context; MBAR_B200_NO_POOL=1 in the environment disables the parking). */
+int mbar_b200_trim(void);
+
 /* ---- context ------------------------------------------------------------------------------- */
 /* N_k: [K] global sample counts as float64 (validate_inputs casts to float, mbar_solvers.py:198). */
 int mbar_b200_create(mbar_b200_ctx** ctx, int device, int32_t K, int64_t N_local, const double* N_k);

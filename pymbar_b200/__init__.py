@@ -11,7 +11,7 @@ from . import _lib
 from .problem import DeviceProblem, PinnedArray
 from .utils import ParameterError
 
-__all__ = ["DeviceProblem", "PinnedArray", "ParameterError", "install", "uninstall", "mbar_solvers"]
+__all__ = ["DeviceProblem", "PinnedArray", "ParameterError", "install", "uninstall", "trim", "mbar_solvers"]
 
 _SAVED = {}
 _PATCHED = (
@@ -45,6 +45,11 @@ def uninstall():
     for (target, name), fn in list(_SAVED.items()):
         setattr(target, name, fn)
         del _SAVED[(target, name)]
+
+
+def trim():
+    """Give back the device / pinned buffers parked by closed DeviceProblems (mbar_b200_trim)."""
+    _lib.check(_lib.load().mbar_b200_trim())
 
 
 def __getattr__(name):

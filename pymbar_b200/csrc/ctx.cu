@@ -11,6 +11,8 @@
 #include <cmath>
 #include <cstring>
 #include <algorithm>
+#include <cstdlib>
+#include <mutex>
 #include <thread>
 
 #include "internal.cuh"
@@ -24,6 +26,45 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------
+// Buffer pool.  The reference's primitives are pure functions of host arrays, so a binding without
+// residency creates and destroys a context per call; cudaFree/cudaMalloc of a 20 GB buffer and
+// cudaHostAlloc of the pinned staging area cost tens to hundreds of ms each.  The largest buffers of a
+// destroyed context are therefore parked (at most one u_kn buffer and one staging set per device) and
+// handed to the next context that fits.  mbar_b200_trim() / MBAR_B200_NO_POOL=1 give the memory back.
+// ------------------------------------------------------------------------------------------
+struct Parked {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+struct DevicePool {
+    Parked u, stageDev[2], stagePin[2];
+};
+static DevicePool g_pool[16];
+static std::mutex g_poolMutex;
+static bool pool_enabled() {
+    static const bool off = std::getenv("MBAR_B200_NO_POOL") != nullptr;
+    return !off;
+}
+// take a parked buffer of at least `bytes` (and at most 2x, so a small problem never pins a huge buffer)
+static void* pool_take(Parked& slot, size_t bytes) {
+    std::lock_guard<std::mutex> g(g_poolMutex);
+    if (slot.ptr && slot.bytes >= bytes && slot.bytes <= 2 * bytes + (1u << 20)) {
+        void* p = slot.ptr;
+        slot = Parked{};
+        return p;
+    }
+    return nullptr;
+}
+// park `ptr`; whatever was parked there before is returned to the caller for release
+static void* pool_park(Parked& slot, void* ptr, size_t bytes) {
+    std::lock_guard<std::mutex> g(g_poolMutex);
+    void* old = slot.ptr;
+    slot.ptr = ptr;
+    slot.bytes = bytes;
+    return old;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -395,7 +436,12 @@ int mbar_b200_create(mbar_b200_ctx** out, int device, int32_t K, int64_t N_local
             return MBAR_B200_ERR_NOMEM;                                        \
         }                                                                      \
     } while (0)
-    ALLOC(c->d_u, uBytes);
+    c->uBytes = uBytes;
+    if (pool_enabled()) {
+        c->d_u = static_cast<double*>(pool_take(g_pool[device & 15].u, uBytes));
+        if (c->d_u) c->uBytes = 0;   // size unknown to this context; keep parking the original size
+    }
+    if (!c->d_u) ALLOC(c->d_u, uBytes);
     ALLOC(c->d_xshift, nPad * sizeof(double));
     ALLOC(c->d_c, 4 * (size_t)K * sizeof(double));
     ALLOC(c->d_Nk, (size_t)K * sizeof(double));
@@ -441,7 +487,25 @@ int mbar_b200_destroy(mbar_b200_ctx* c) {
     for (void* pm : c->peerMapped) cudaIpcCloseMemHandle(pm);
     cudaFree(c->d_inbox);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_u); cudaFree(c->d_xshift); cudaFree(c->d_wgt); cudaFree(c->d_sqrtw); cudaFree(c->d_c); cudaFree(c->d_Nk); cudaFree(c->d_NkEff);
+    if (pool_enabled() && c->d_u) {
+        // (a buffer taken from the pool may be larger than this context needed: park it with the size
+        // it is known to cover at least)
+        const size_t need = (size_t)c->nTiles * c->K * TILE_N * sizeof(double);
+        cudaFree(pool_park(g_pool[c->device & 15].u, c->d_u, c->uBytes ? c->uBytes : need));
+        for (int i = 0; i < 2; ++i) {
+            const size_t sb = (size_t)c->stageCols * c->K * sizeof(double);
+            if (c->stage_dev[i]) cudaFree(pool_park(g_pool[c->device & 15].stageDev[i], c->stage_dev[i], sb));
+            if (c->stage_pinned[i]) {
+                void* old = pool_park(g_pool[c->device & 15].stagePin[i], c->stage_pinned[i], sb);
+                if (old) cudaFreeHost(old);
+            }
+            c->stage_dev[i] = nullptr;
+            c->stage_pinned[i] = nullptr;
+        }
+    } else {
+        cudaFree(c->d_u);
+    }
+    cudaFree(c->d_xshift); cudaFree(c->d_wgt); cudaFree(c->d_sqrtw); cudaFree(c->d_c); cudaFree(c->d_Nk); cudaFree(c->d_NkEff);
     cudaFree(c->d_rowmask); cudaFree(c->d_zeromask); cudaFree(c->d_onesmask); cudaFree(c->d_partial); cudaFree(c->d_out); cudaFree(c->d_L);
     cudaFree(c->d_W); cudaFree(c->d_ticket); cudaFree(c->d_flag); cudaFree(c->d_f);
     cudaFree(c->d_scratch);
@@ -458,6 +522,31 @@ int mbar_b200_destroy(mbar_b200_ctx* c) {
     if (c->copyStream) cudaStreamDestroy(c->copyStream);
     cudaGetLastError();
     delete c;
+    return MBAR_B200_OK;
+}
+
+int mbar_b200_trim(void) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < 16; ++d) {
+        DevicePool old;
+        {
+            std::lock_guard<std::mutex> g(g_poolMutex);
+            old = g_pool[d];
+            g_pool[d] = DevicePool{};
+        }
+        if (!old.u.ptr && !old.stageDev[0].ptr && !old.stageDev[1].ptr && !old.stagePin[0].ptr &&
+            !old.stagePin[1].ptr)
+            continue;
+        cudaSetDevice(d);
+        cudaFree(old.u.ptr);
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(old.stageDev[i].ptr);
+            if (old.stagePin[i].ptr) cudaFreeHost(old.stagePin[i].ptr);
+        }
+    }
+    cudaSetDevice(cur);
+    cudaGetLastError();
     return MBAR_B200_OK;
 }
 
@@ -503,7 +592,11 @@ static int ensure_staging(mbar_b200_ctx* c, bool needPinned) {
     }
     const size_t bytes = (size_t)c->stageCols * c->K * sizeof(double);
     for (int i = 0; i < 2; ++i) {
+        if (!c->stage_dev[i] && pool_enabled())
+            c->stage_dev[i] = static_cast<double*>(pool_take(g_pool[c->device & 15].stageDev[i], bytes));
         if (!c->stage_dev[i]) MBAR_CUDA(cudaMalloc((void**)&c->stage_dev[i], bytes));
+        if (needPinned && !c->stage_pinned[i] && pool_enabled())
+            c->stage_pinned[i] = static_cast<double*>(pool_take(g_pool[c->device & 15].stagePin[i], bytes));
         if (needPinned && !c->stage_pinned[i])
             MBAR_CUDA(cudaHostAlloc((void**)&c->stage_pinned[i], bytes, cudaHostAllocDefault));
     }

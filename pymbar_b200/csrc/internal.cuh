@@ -84,6 +84,7 @@ struct mbar_b200_ctx {
     double N_total_states = 0;      // sum_k N_k (global N)
 
     double* d_u = nullptr;          // [nTiles][K][32] shifted, clamped
+    size_t uBytes = 0;              // bytes this context allocated for d_u (0: came from the pool)
     double* d_xshift = nullptr;     // [nTiles*32] per-sample shift x_n = min over sampled k of u_kn
     double* d_wgt = nullptr;        // [nTiles*32] per-sample multiplicities w_n (bootstrap), or NULL = all 1
     double* d_sqrtw = nullptr;      // [nTiles*32] sqrt(w_n) for the second-moment kernel
