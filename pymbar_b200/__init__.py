@@ -24,7 +24,7 @@ _PATCHED = (
 )
 
 
-def install(target=None):
+def install(target=None, patch_layout_helpers=True):
     """Route ``pymbar.mbar_solvers`` (or `target`, a module object) through the B200 backend.
 
     pymbar looks its solver entry points up as module attributes at call time (mbar.py:413, :437,
@@ -38,6 +38,18 @@ def install(target=None):
         if hasattr(target, name) and (target, name) not in _SAVED:
             _SAVED[(target, name)] = getattr(target, name)
         setattr(target, name, getattr(backend, name))
+    if patch_layout_helpers and target.__name__ == "pymbar.mbar_solvers":
+        # MBAR.__init__ converts 3-D input with a per-column Python loop (mbar.py:238, utils.py:68-71);
+        # it looks the helper up in its own module namespace
+        import pymbar.mbar as mbar_mod
+
+        from . import utils as u
+
+        for name in ("kln_to_kn", "kn_to_n"):
+            if hasattr(mbar_mod, name):
+                if (mbar_mod, name) not in _SAVED:
+                    _SAVED[(mbar_mod, name)] = getattr(mbar_mod, name)
+                setattr(mbar_mod, name, getattr(u, name))
     return target
 
 

@@ -28,8 +28,13 @@ def test_install_rebinds_real_pymbar_when_available():
         assert ref_ms.solve_mbar_for_all_states is ours.solve_mbar_for_all_states
         assert ref_ms.mbar_log_W_nk is ours.mbar_log_W_nk and ref_ms.jax_mbar_gradient is ours.mbar_gradient
         assert ref_ms.DEFAULT_SOLVER_PROTOCOL == ours.DEFAULT_SOLVER_PROTOCOL
+        import pymbar.mbar as mbar_mod
+        from pymbar_b200 import utils as ours_utils
+
+        assert mbar_mod.kln_to_kn is ours_utils.kln_to_kn
         pymbar_b200.uninstall()
         assert ref_ms.solve_mbar_for_all_states is orig
+        assert mbar_mod.kln_to_kn is not ours_utils.kln_to_kn
     finally:
         sys.path.remove("/root/reference")
         sys.path.remove(os.path.join(ROOT, "oracle", "ref_shim"))
