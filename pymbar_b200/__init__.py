@@ -38,6 +38,19 @@ def install(target=None, patch_layout_helpers=True):
         if hasattr(target, name) and (target, name) not in _SAVED:
             _SAVED[(target, name)] = getattr(target, name)
         setattr(target, name, getattr(backend, name))
+    if target.__name__ == "pymbar.mbar_solvers":
+        # raise pymbar's own exception type so that `except pymbar.utils.ParameterError` keeps working
+        try:
+            from pymbar.utils import ParameterError as _PE
+
+            from . import utils as _u
+
+            if ("ParameterError",) not in _SAVED:
+                _SAVED[("ParameterError",)] = (backend.ParameterError, _u.ParameterError)
+            backend.ParameterError = _PE
+            _u.ParameterError = _PE
+        except ImportError:
+            pass
     if patch_layout_helpers and target.__name__ == "pymbar.mbar_solvers":
         # MBAR.__init__ converts 3-D input with a per-column Python loop (mbar.py:238, utils.py:68-71);
         # it looks the helper up in its own module namespace
@@ -54,9 +67,15 @@ def install(target=None, patch_layout_helpers=True):
 
 
 def uninstall():
-    for (target, name), fn in list(_SAVED.items()):
-        setattr(target, name, fn)
-        del _SAVED[(target, name)]
+    for key, fn in list(_SAVED.items()):
+        if key == ("ParameterError",):
+            from . import mbar_solvers as backend
+            from . import utils as _u
+
+            backend.ParameterError, _u.ParameterError = fn
+        else:
+            setattr(key[0], key[1], fn)
+        del _SAVED[key]
 
 
 def trim():
