@@ -1,0 +1,22 @@
+"""The reference's own solver tests (pymbar/tests/test_mbar_solvers.py, test_mbar.py — SURVEY.md §4: the
+acceptance set for this path) run unmodified against the mirror's driver layer (device replaced by the
+oracle stand-in).  Build container only: needs /root/reference."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/pymbar/tests"), reason="reference checkout not present")
+def test_reference_solver_tests_pass_on_the_mirror(tmp_path):
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([ROOT, os.path.join(ROOT, "oracle", "ref_shim"), "/root/reference"])
+    cmd = [sys.executable, "-m", "pytest", "-q", "-p", "tests._mirror_plugin", "-p", "no:cacheprovider",
+           "/root/reference/pymbar/tests/test_mbar_solvers.py", "/root/reference/pymbar/tests/test_mbar.py"]
+    out = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=1500)
+    tail = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-500:]
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert " passed" in tail and "failed" not in tail, tail
