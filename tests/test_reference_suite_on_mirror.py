@@ -19,4 +19,4 @@ def test_reference_solver_tests_pass_on_the_mirror(tmp_path):
     out = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=1500)
     tail = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-500:]
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
-    assert " passed" in tail and "failed" not in tail, tail
+    assert " passed" in tail and " failed" not in tail and " error" not in tail, tail
