@@ -175,6 +175,7 @@ int mbar_b200_self_consistent_update_host(int device, int32_t K, int64_t N, cons
 /* ---- multi-GPU: samples sharded over ranks, one all-reduce per pass -------------------------- */
 #define MBAR_B200_UNIQUE_ID_BYTES 128
 int mbar_b200_comm_unique_id(void* id_out /* [128] */);
+/* Collective over all ranks; call it after this rank's u_kn is uploaded / synthesised. */
 int mbar_b200_comm_init(mbar_b200_ctx* ctx, int32_t nranks, int32_t rank, const void* unique_id);
 int mbar_b200_comm_destroy(mbar_b200_ctx* ctx);
 

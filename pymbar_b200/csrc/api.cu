@@ -146,7 +146,9 @@ static int run_pass(mbar_b200_ctx* c, const double* f, PassWant want) {
         if (!fused) MBAR_TRY(launch_pass_generic(c, f, wantL, logAll));
         // S | sumL | flag are sums over samples -> one all-reduce
         MBAR_TRY(comm_allreduce(c, c->d_out, K + 2, 0));
-        if ((needUnsampled || logAll) && c->comm && c->nranks > 1) {
+        // log-domain partial sums (generic kernel only) are combined across ranks by max + rescaled sum;
+        // the fused kernel's linear sums for unsampled states went through the all-reduce above
+        if (((needUnsampled && !fused) || logAll) && c->comm && c->nranks > 1) {
             double* mx = c->d_scratch;
             double* sc = c->d_scratch + K;
             MBAR_CUDA(cudaMemcpyAsync(mx, c->d_out + lay.logS(), K * sizeof(double),
@@ -724,6 +726,15 @@ int mbar_b200_comm_init(mbar_b200_ctx* c, int32_t nranks, int32_t rank, const vo
     c->comm = comm;
     c->nranks = nranks;
     c->rank = rank;
+    // kernel-selection inputs must be identical on every rank (all ranks issue the same collectives)
+    {
+        double flag = c->unsampledExtreme ? 1.0 : 0.0;
+        MBAR_CUDA(cudaMemcpyAsync(c->d_scratch, &flag, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        MBAR_TRY(comm_allreduce(c, c->d_scratch, 1, 2));
+        MBAR_CUDA(cudaMemcpyAsync(&flag, c->d_scratch, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        MBAR_CUDA(cudaStreamSynchronize(c->stream));
+        c->unsampledExtreme = flag != 0.0;
+    }
     return MBAR_B200_OK;
 }
 
