@@ -289,3 +289,30 @@ def test_one_shot_host_entry(lib):
                                                            out.ctypes.data_as(dp))
     assert rc == 0
     np.testing.assert_allclose(out, z["rand_sci"], atol=1e-10)
+
+
+def test_context_housekeeping(lib):
+    """get_shape, counters, the parked-buffer pool and trim()."""
+    import ctypes as C
+
+    from pymbar_b200 import _lib
+
+    z = _cases.load("small_osc_8x40")
+    N = z["N_k"].astype(float)
+    p = lib.DeviceProblem(z["u_kn"], N)
+    K, Nl = C.c_int32(0), C.c_int64(0)
+    assert _lib.load().mbar_b200_get_shape(p._h, C.byref(K), C.byref(Nl)) == 0
+    assert (K.value, Nl.value) == z["u_kn"].shape
+    before = p.counters()
+    p.gradient(np.zeros(len(N)))
+    after = p.counters()
+    assert after["passes"] == before["passes"] + 1 and after["launches"] > before["launches"]
+    want = p.self_consistent_update(z["f_rand"])
+    p.close()
+    q = lib.DeviceProblem(z["u_kn"], N)            # reuses the parked buffers
+    np.testing.assert_array_equal(q.self_consistent_update(z["f_rand"]), want)
+    q.close()
+    lib.trim()
+    r = lib.DeviceProblem(z["u_kn"], N)            # fresh allocations after trim
+    np.testing.assert_array_equal(r.self_consistent_update(z["f_rand"]), want)
+    r.close()
