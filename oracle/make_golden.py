@@ -31,19 +31,24 @@ from oracle import testsystems as ots  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
+LAST_X = [None]   # positions of the most recently sampled test system (observable for expectations)
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
 def ref_harmonic(O_k, K_k, N_k, seed):
     tc = ref_ts.harmonic_oscillators.HarmonicOscillatorsTestCase(O_k=O_k, K_k=K_k)
-    _, u_kn, N_out, _ = tc.sample(N_k, mode="u_kn", seed=seed)
+    x_n, u_kn, N_out, _ = tc.sample(N_k, mode="u_kn", seed=seed)
+    LAST_X[0] = np.array(x_n)
     return u_kn, np.asarray(N_out)
 
 
 def ref_exponential(rates, N_k, seed):
     tc = ref_ts.exponential_distributions.ExponentialTestCase(rates)
-    _, u_kn, N_out, _ = tc.sample(N_k, mode="u_kn", seed=seed)
+    x_n, u_kn, N_out, _ = tc.sample(N_k, mode="u_kn", seed=seed)
+    LAST_X[0] = np.array(x_n)
     return u_kn, np.asarray(N_out)
 
 
@@ -112,6 +117,20 @@ def case(name, u_kn, N_k, store_u, regen, rng):
         W = np.exp(m.Log_W_nk)
         data["est_G"] = W.T @ W
     if store_u:
+        # expectations / perturbed free energies (mbar.py:1124, :1442) at the default solution
+        me = pymbar.MBAR(u_kn, N_k)
+        x_n = LAST_X[0]
+        data["x_n"] = x_n.copy()
+        r = me.compute_expectations(x_n.copy())           # (the reference shifts A_n in place)
+        data["expt_avg_mu"], data["expt_avg_sigma"] = np.array(r["mu"]), np.array(r["sigma"])
+        r = me.compute_expectations(x_n.copy(), output="differences")
+        data["expt_diff_mu"], data["expt_diff_sigma"] = np.array(r["mu"]), np.array(r["sigma"])
+        r = me.compute_expectations(u_kn.copy(), state_dependent=True)
+        data["expt_sd_mu"], data["expt_sd_sigma"] = np.array(r["mu"]), np.array(r["sigma"])
+        u_ln = np.vstack([0.5 * (u_kn[0] + u_kn[1]), 1.3 * u_kn[-1], u_kn[0] + 0.2 * x_n])
+        data["pert_u_ln"] = u_ln
+        r = me.compute_perturbed_free_energies(u_ln.copy())
+        data["pert_Delta_f"], data["pert_dDelta_f"] = np.array(r["Delta_f"]), np.array(r["dDelta_f"])
         # bootstrap replicates (mbar.py:417-449) with a fixed rseed: indices and the re-solved f_k
         mb = pymbar.MBAR(u_kn, N_k, n_bootstraps=4, rseed=11)
         data["boot_rints"] = np.array(mb.bootstrap_rints)
