@@ -54,7 +54,7 @@ typedef enum mbar_b200_status {
 /* Which kernel family a pass uses (mbar_b200_set_pass_kernel). AUTO = fused when it applies. */
 typedef enum mbar_b200_kernel {
     MBAR_B200_KERNEL_AUTO = 0,
-    MBAR_B200_KERNEL_FUSED = 1,      /* TMA-pipelined persistent kernel, K <= 256                          */
+    MBAR_B200_KERNEL_FUSED = 1,      /* TMA-pipelined persistent kernel (clusters of CTAs above K = 256), K <= 2048 */
     MBAR_B200_KERNEL_GENERIC = 2     /* any K, log-domain for unsampled states                            */
 } mbar_b200_kernel;
 

@@ -47,7 +47,7 @@ __device__ __forceinline__ void convert_row(double* P, int row, int lane, double
 // they get 3/4 of the CTAs an off-diagonal pair gets.
 struct HessSplit {
     int nPairs;
-    int pairStart[40];
+    int pairStart[140];
 };
 
 __global__ void __launch_bounds__(512, 1)
@@ -241,7 +241,7 @@ int launch_hessian(mbar_b200_ctx* ctx, const double* h_f, bool allRows) {
                               cudaMemcpyHostToDevice, ctx->stream));
     const int nB = (K + HB - 1) / HB;
     const int nPairs = nB * (nB + 1) / 2;
-    MBAR_REQUIRE(nPairs < 40, MBAR_B200_ERR_INVALID, "K=%d too large for the Hessian kernel (K <= 1024)", K);
+    MBAR_REQUIRE(nPairs < 140, MBAR_B200_ERR_INVALID, "K=%d too large for the Hessian kernel (K <= 2048)", K);
     // CTAs per pair proportional to its cost per tile (4 for off-diagonal, 3 for diagonal pairs)
     HessSplit split{};
     split.nPairs = nPairs;

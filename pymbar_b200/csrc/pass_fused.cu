@@ -34,12 +34,13 @@
 namespace mbar {
 
 
-constexpr int FUSED_MAX_CW = 16;   // consumer warps: 8 (R <= 32 rows/thread) or 16 (R <= 16)
+// denominator-exchange slots per parity: 16 inside one CTA, CL * 8 across a cluster of CL CTAs
+__host__ __device__ constexpr int fused_slots(int CL) { return CL > 1 ? CL * 8 : 16; }
 constexpr uint32_t FUSED_COPY_CHUNK = 32768;
 
-__host__ __device__ inline size_t fused_smem_header(int K) {
-    // tab[32] | c_s[K] | xD[2][16][32] | sred[256] | sumL[16] | bad[16] | full[8] | empty[8]
-    size_t b = 256 + (size_t)K * 8 + 2 * FUSED_MAX_CW * 32 * 8 + 256 * 8 + 128 + 128 + 64 + 64;
+__host__ __device__ inline size_t fused_smem_header(int K, int CL) {
+    // tab[32] | c_s[K] | xD[2][slots][32] | sred[256] | sumL[16] | bad[16] | full[8] | empty[8]
+    size_t b = 256 + (size_t)K * 8 + 2 * (size_t)fused_slots(CL) * 32 * 8 + 256 * 8 + 128 + 128 + 64 + 64;
     return (b + 127) & ~(size_t)127;
 }
 
@@ -184,27 +185,28 @@ __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// CL = 1: one CTA per tile group, K <= 256.  CL = 2 (256 < K <= 512): a cluster of two CTAs works on the
-// same tile; CTA `half` owns states [half*Kh, ...), pulls only those rows from HBM (no redundant
-// traffic) and the per-sample denominators are completed by exchanging the warps' partial sums
-// through distributed shared memory + one cluster barrier per tile.
+// CL = 1: one CTA per tile group, K <= 256.  CL = 2, 4, 8 (K <= 512, 1024, 2048): a cluster of CL CTAs (CL
+// SMs) works on the same tile; CTA `half` (its rank in the cluster) owns states [half*Kh, ...), pulls only
+// those rows from HBM (no redundant traffic) and the per-sample denominators are completed by exchanging
+// the warps' partial sums through distributed shared memory + one cluster barrier per tile.
 template <int R, bool FULL, int CW, int BATCH, int MODE, int CL>
 __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int K = p.K;
-    const int half = (CL == 2) ? (int)cluster_ctarank() : 0;
-    const int kbase = (CL == 2) ? half * p.Kh : 0;                       // first state of this CTA
-    const int Kl = (CL == 2) ? (half ? K - p.Kh : p.Kh) : K;            // states of this CTA
+    const int half = (CL > 1) ? (int)cluster_ctarank() : 0;             // rank of this CTA in its cluster
+    const int kbase = (CL > 1) ? half * p.Kh : 0;                        // first state of this CTA
+    const int Kl = (CL > 1) ? max(0, min(p.Kh, K - kbase)) : K;         // states of this CTA
     const unsigned nGroups = gridDim.x / CL, grp = blockIdx.x / CL;      // CTA (pair) index
     double* tab = reinterpret_cast<double*>(smem_raw);
     double* c_s = tab + 32;
     double* xD = c_s + K;                        // [2][CW warps][32]
-    double* sred = xD + 2 * FUSED_MAX_CW * 32;   // [Wn][K]  (Wn * K <= 256)
+    constexpr int SLOTS = fused_slots(CL);
+    double* sred = xD + 2 * SLOTS * 32;          // [Wn][K]  (Wn * K <= 256)
     double* s_sumL = sred + 256;                 // [16]
     int* s_bad = reinterpret_cast<int*>(s_sumL + 16);         // [16] (+pad)
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_sumL + 32);
     uint64_t* bar_empty = bar_full + 8;
-    unsigned char* stages = smem_raw + fused_smem_header(K);
+    unsigned char* stages = smem_raw + fused_smem_header(K, CL);
     __shared__ bool s_last;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
     for (int k = threadIdx.x; k < Kl; k += blockDim.x)
         c_s[k] = (MODE & 2) ? exp(p.c[kbase + k]) : p.c[kbase + k];
     // masked variants read up to 31 state constants past this CTA's rows: keep those bytes finite
-    for (int i = threadIdx.x; i < 2 * FUSED_MAX_CW * 32; i += blockDim.x) xD[i] = 0.0;
+    for (int i = threadIdx.x; i < 2 * SLOTS * 32; i += blockDim.x) xD[i] = 0.0;
     // lane-replicated exp table, 8 KB aligned so that its address bits never overlap the index bits
     const uint32_t tabRep = (smem_u32(stages + (size_t)p.NS * p.stageBytes) + 8191u) & ~8191u;
     if (MODE & 1)
@@ -249,7 +251,9 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
         const int64_t ntl = min((int64_t)tilesPerStage, p.nTiles - tile0);
         const uint32_t fb = smem_u32(&bar_full[slot2]);
         const uint32_t dst = smem_u32(stages + (size_t)slot2 * p.stageBytes);
-        if (CL == 1) {
+        if (Kl <= 0) {
+            mbar_arrive_expect_tx(fb, 0);                           // (a trailing CTA without states)
+        } else if (CL == 1) {
             const uint32_t bytes = (uint32_t)ntl * p.tileBytes;     // whole tiles are contiguous
             mbar_arrive_expect_tx(fb, bytes);
             const unsigned char* src =
@@ -317,17 +321,18 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                     exp_rows<R, B, 0, MODE, !FULL>(cA, uA, cB, uB, tr, e, Dp, c_s + k0, tp, actbits);
                 }
                 double D = Dp;
-                if (CL == 2) {
-                    // 16 partial sums per sample: slot = owner half * 8 + warp, written locally and into
-                    // the partner CTA's shared memory; both CTAs then add them in the same order
-                    double* x = xD + (par * FUSED_MAX_CW + half * 8 + w) * 32 + lane;
+                if (CL > 1) {
+                    // CL*8 partial sums per sample: slot = owner rank * 8 + warp, written locally and into
+                    // every partner CTA's shared memory; all CTAs then add them in the same order
+                    double* x = xD + (par * SLOTS + half * 8 + w) * 32 + lane;
                     *x = Dp;
-                    st_cluster_f64(x, (unsigned)(half ^ 1), Dp);
+#pragma unroll
+                    for (int q = 1; q < CL; ++q) st_cluster_f64(x, (unsigned)((half + q) % CL), Dp);
                     cluster_barrier();
-                    const double* xs = xD + par * FUSED_MAX_CW * 32 + lane;
+                    const double* xs = xD + par * SLOTS * 32 + lane;
                     D = 0.0;
 #pragma unroll
-                    for (int ww = 0; ww < 16; ++ww) D += xs[ww * 32];
+                    for (int ww = 0; ww < CL * 8; ++ww) D += xs[ww * 32];
                     par ^= 1;
                 } else if (p.Wk > 1) {
                     double* x = xD + (par * CW + g * p.Wk) * 32 + lane;
@@ -372,7 +377,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
             s_bad[warp] = bad;
         }
     }
-    if (CL == 2) cluster_barrier();   // the partner may not exit while it can still be written to
+    if (CL > 1) cluster_barrier();    // a partner may not exit while it can still be written to
     __syncthreads();
 
     double* P = p.partial + (size_t)grp * (K + 2);
@@ -486,7 +491,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
 
 bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, bool allStates, double* midOut,
                       double* spreadOut) {
-    if (ctx->K > 512) return false;
+    if (ctx->K > 2048) return false;
     if (allStates && ctx->unsampledExtreme) return false;
     double lo = INFINITY, hi = -INFINITY;
     for (int k = 0; k < ctx->K; ++k) {
@@ -521,8 +526,9 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allSta
     p.allStates = allStates ? 1 : 0;
     const int cw = 8;
     const int rmax = 32;
-    p.CL = K > 256 ? 2 : 1;                  // 256 < K <= 512: two-CTA clusters, half the states each
-    p.Kh = p.CL == 2 ? (K + 1) / 2 : K;
+    p.CL = K > 1024 ? 8 : K > 512 ? 4 : K > 256 ? 2 : 1;   // clusters of CL CTAs, K/CL states each
+    p.Kh = (K + p.CL - 1) / p.CL;
+    if (p.CL > 1) p.Kh = (p.Kh + 1) & ~1;   // even split point: 16-byte aligned pairs of state constants
     int wk = 1;
     while (wk * rmax < p.Kh) wk *= 2;
     p.Wk = wk;
@@ -538,8 +544,8 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allSta
     int tpw = (int)(65536u / (p.Wn * ctaTileBytes));
     p.TPW = tpw < 1 ? 1 : (tpw > 8 ? 8 : tpw);
     p.stageBytes = (uint32_t)p.Wn * p.TPW * ctaTileBytes;
-    const size_t header = fused_smem_header(K);
-    int ns = (int)((225 * 1024 - header - 16384) / p.stageBytes);
+    const size_t header = fused_smem_header(K, p.CL);
+    int ns = (int)((225 * 1024 - header - 16384) / p.stageBytes);   // (CL >= 4 -> 2 stages of 64 KB)
     p.NS = ns > 8 ? 8 : ns;
     if (p.NS < 2) return MBAR_B200_OK;
     const int tilesPerStage = p.Wn * p.TPW;
@@ -572,7 +578,7 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allSta
 
 // Launch with whatever c currently sits in ctx->d_c (device-resident iteration).
 int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
-    const size_t smem = fused_smem_header(p.K) + (size_t)p.NS * p.stageBytes + 16384;
+    const size_t smem = fused_smem_header(p.K, p.CL) + (size_t)p.NS * p.stageBytes + 16384;
     int64_t grid = p.nStages < ctx->smCount / p.CL ? p.nStages : ctx->smCount / p.CL;
     grid *= p.CL;
     const int Rt = p.Rw <= 8 ? 8 : p.Rw <= 16 ? 16 : 32;
@@ -587,10 +593,10 @@ int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
         else if (!(p.mode & 2)) { kern = pass_fused_kernel<R_, true, 8, 8, 1, CL_>; which = ID_ + 2; } \
         else { kern = pass_fused_kernel<R_, true, 8, 8, 3, CL_>; which = ID_ + 3; }                    \
     }
-    PICK(8, 1, 0) PICK(16, 1, 4) PICK(32, 1, 8) PICK(32, 2, 12)
+    PICK(8, 1, 0) PICK(16, 1, 4) PICK(32, 1, 8) PICK(32, 2, 12) PICK(32, 4, 16) PICK(32, 8, 20)
 #undef PICK
     MBAR_REQUIRE(kern, MBAR_B200_ERR_INVALID, "no fused kernel variant for K=%d", p.K);
-    static size_t attrSetAll[16][20] = {{0}};          // per device: the attribute belongs to the context
+    static size_t attrSetAll[16][24] = {{0}};          // per device: the attribute belongs to the context
     size_t* attrSet = attrSetAll[ctx->device & 15];
     if (attrSet[which] < smem) {
         MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -607,7 +613,7 @@ int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
         cfg.stream = ctx->stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.x = (unsigned)p.CL;
         at[0].val.clusterDim.y = 1;
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;

@@ -190,9 +190,10 @@ def test_large_energy_offsets(lib):
     np.testing.assert_allclose(f - off, z["fk_default"], atol=1e-7)
 
 
-@pytest.mark.parametrize("K,n", [(512, 12), (300, 20), (257, 8), (384, 10)])
+@pytest.mark.parametrize("K,n", [(512, 12), (300, 20), (257, 8), (384, 10), (513, 4), (700, 3), (1024, 3),
+                                 (1025, 2), (1500, 2), (2048, 2)])
 def test_two_cta_cluster_kernel(lib, K, n):
-    """256 < K <= 512: the fused kernel runs as clusters of two CTAs (half the states each, partial
+    """256 < K <= 2048: the fused kernel runs as clusters of 2 / 4 / 8 CTAs (K/CL states each, partial
     denominators exchanged through distributed shared memory).  Checked against the oracle."""
     from oracle import testsystems as ots
 

@@ -1,4 +1,4 @@
-"""Randomised shape sweep (GPU): K in [1, 520], N in [1, 4000], empty states at random, random f_k and
+"""Randomised shape sweep (GPU): K in [1, 2100], N in [1, 4000], empty states at random, random f_k and
 random per-sample multiplicities — every primitive against the oracle.  Seeds are fixed; the sweep is
 deterministic.  Catches tiling / masking / tail-stage edge cases that hand-picked shapes miss."""
 import numpy as np
@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 def _case(seed):
     rng = np.random.RandomState(seed)
     K = int(rng.choice([1, 2, 3, 5, 8, 9, 16, 17, 31, 32, 33, 48, 63, 64, 65, 100, 127, 128, 129, 200, 255, 256,
-                        257, 300, 384, 511, 512, 513, 520]))
+                        257, 300, 384, 511, 512, 513, 520, 777, 1024, 1100, 2048, 2100]))
     per = int(rng.randint(1, max(2, 4000 // K)))
     N_k = rng.randint(0, per + 1, size=K)
     if rng.rand() < 0.5:
@@ -30,7 +30,7 @@ def _case(seed):
     return K, N, N_k, u, f, rng
 
 
-@pytest.mark.parametrize("seed", range(36))
+@pytest.mark.parametrize("seed", range(48))
 def test_random_shape(seed):
     import pymbar_b200
 
