@@ -89,3 +89,25 @@ def test_shard_additivity_and_k512(lib):
         S_o, _ = orc.single_pass_sums(sl, N_k, f)
         np.testing.assert_allclose(Sq, S_o, rtol=1e-11)
     p.close()
+
+
+def test_c5_per_gpu_shard_shape(lib):
+    """BASELINE.json configs[4] per GPU: K = 512, N = 1.25e7 (51.2 GB of u_kn in HBM).  One device-resident
+    self-consistent iteration from the analytic free energies must stay at them to statistical accuracy,
+    sum_n W_nk must be ~1 there, and a downloaded slice must agree with the oracle."""
+    K, N = 512, 12_500_000
+    p, N_k, O, kk = _problem(lib, K, N, seed=1)
+    try:
+        fa = ots.harmonic_analytical_f_k(kk)
+        S, sumL, _ = p.streaming_pass(fa)
+        assert np.max(np.abs(S - 1.0)) < 0.02
+        f1 = p.sci_iterate(fa, 1)
+        assert np.max(np.abs(f1 - fa)) < 0.02
+        sl = p.download(N - 4096 - 7, 4096)
+        with lib.DeviceProblem(sl, N_k) as q:
+            Sq, _, _ = q.streaming_pass(fa)
+            S_o, _ = orc.single_pass_sums(sl, N_k, fa)
+            np.testing.assert_allclose(Sq, S_o, rtol=1e-11)
+        assert p.last_pass_ms() < 60.0
+    finally:
+        p.close()
