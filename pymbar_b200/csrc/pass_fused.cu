@@ -39,8 +39,9 @@ __host__ __device__ constexpr int fused_slots(int CL) { return CL > 1 ? CL * 8 :
 constexpr uint32_t FUSED_COPY_CHUNK = 32768;
 
 __host__ __device__ inline size_t fused_smem_header(int K, int CL) {
-    // tab[32] | c_s[K] | xD[2][slots][32] | sred[256] | sumL[16] | bad[16] | full[8] | empty[8]
-    size_t b = 256 + (size_t)K * 8 + 2 * (size_t)fused_slots(CL) * 32 * 8 + 256 * 8 + 128 + 128 + 64 + 64;
+    // tab[32] | c_s[K + 32] | xD[2][slots][32] | sred[256] | sumL[16] | bad[16] | full[8] | empty[8]
+    // (c_s carries 32 spare entries: the masked variants fetch constants of up to 31 rows they do not own)
+    size_t b = 256 + ((size_t)K + 32) * 8 + 2 * (size_t)fused_slots(CL) * 32 * 8 + 256 * 8 + 128 + 128 + 64 + 64;
     return (b + 127) & ~(size_t)127;
 }
 
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
     const unsigned nGroups = gridDim.x / CL, grp = blockIdx.x / CL;      // CTA (pair) index
     double* tab = reinterpret_cast<double*>(smem_raw);
     double* c_s = tab + 32;
-    double* xD = c_s + K;                        // [2][CW warps][32]
+    double* xD = c_s + K + 32;                   // [2][slots][32]
     constexpr int SLOTS = fused_slots(CL);
     double* sred = xD + 2 * SLOTS * 32;          // [Wn][K]  (Wn * K <= 256)
     double* s_sumL = sred + 256;                 // [16]
@@ -214,7 +215,8 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
     // state constants: c_k, or E_k = exp(c_k) when the constant is applied multiplicatively
     for (int k = threadIdx.x; k < Kl; k += blockDim.x)
         c_s[k] = (MODE & 2) ? exp(p.c[kbase + k]) : p.c[kbase + k];
-    // masked variants read up to 31 state constants past this CTA's rows: keep those bytes finite
+    // masked variants read up to 31 state constants past this CTA's rows: keep those entries finite
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) c_s[Kl + i] = 0.0;
     for (int i = threadIdx.x; i < 2 * SLOTS * 32; i += blockDim.x) xD[i] = 0.0;
     // lane-replicated exp table, 8 KB aligned so that its address bits never overlap the index bits
     const uint32_t tabRep = (smem_u32(stages + (size_t)p.NS * p.stageBytes) + 8191u) & ~8191u;
@@ -229,6 +231,9 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
         mbar_fence_init();
     }
     __syncthreads();
+    // distributed shared memory may only be touched once every CTA of the cluster is running, and a
+    // partner's first remote store must not land before this CTA has finished initialising xD
+    if (CL > 1) cluster_barrier();
 
     const int tilesPerStage = p.Wn * p.TPW;
     double acc[R];
@@ -544,6 +549,14 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allSta
     int tpw = (int)(65536u / (p.Wn * ctaTileBytes));
     p.TPW = tpw < 1 ? 1 : (tpw > 8 ? 8 : tpw);
     p.stageBytes = (uint32_t)p.Wn * p.TPW * ctaTileBytes;
+    {
+        // the masked variants read (and discard) up to R rows per warp regardless of how many it owns:
+        // pad every ring slot so that those reads never touch a slot the TMA engine may be filling
+        const int rt = p.Rw <= 8 ? 8 : p.Rw <= 16 ? 16 : 32;
+        const int over = (p.Wk - 1) * p.Rw + rt - p.Kh;          // rows past the CTA's last state
+        if (over > 0) p.stageBytes += (uint32_t)over * TILE_N * 8;
+        p.stageBytes = (p.stageBytes + 127u) & ~127u;
+    }
     const size_t header = fused_smem_header(K, p.CL);
     int ns = (int)((225 * 1024 - header - 16384) / p.stageBytes);   // (CL >= 4 -> 2 stages of 64 KB)
     p.NS = ns > 8 ? 8 : ns;
