@@ -173,6 +173,25 @@ def time_cpu_reference(K, budget_s, steps, warmup):
     return u.size / per_step, per_step, u.shape[1]
 
 
+def time_c_port(K, n_sample=400_000):
+    """The C/pthreads restatement of the same two sweeps with every host thread: context beside the
+    single-threaded numpy port (which is what the reference's own implementation is)."""
+    try:
+        from oracle import c_oracle
+
+        u, N_k = cpu_sample(K, n_sample)
+        f = np.zeros(K)
+        c_oracle.self_consistent_update(u, N_k, f)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            c_oracle.self_consistent_update(u, N_k, f)
+        dt = (time.perf_counter() - t0) / 3
+        return {"value": u.size / dt, "unit": UNIT, "threads": c_oracle.threads(),
+                "what": "oracle/mbar_oracle.c (pthreads), same arithmetic, all host threads"}
+    except Exception as exc:  # pragma: no cover
+        return {"unavailable": str(exc)[:200]}
+
+
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
@@ -194,6 +213,7 @@ def run_reference(args):
                    "K": K, "N_sample": n_sample, "flush": "n/a (CPU)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
                          "host_cpus": os.cpu_count(), "blas_threads": blas,
+                         "c_port_all_threads": time_c_port(K),
                          "sample": f"self_consistent_update (numpy oracle port of mbar_solvers.py:231-242, "
                                    f"scipy.special.logsumexp x2, single-threaded like the reference) on K={K}, "
                                    f"N={n_sample} of the same harmonic family; throughput is flat in N (BASELINE.md §2)"},
@@ -358,6 +378,7 @@ def run_ours(args):
                          "how": "per-launch cudaEvent pairs recorded around the kernel inside the timed loop"},
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
                              "host_cpus": os.cpu_count(),
+                             "c_port_all_threads": time_c_port(K),
                              "sample": f"numpy oracle self_consistent_update on K={K}, N={n_sample} of the same "
                                        f"family ({cpu_step:.2f} s/step); reference is single-threaded numpy"},
             "e2e": e2e,
