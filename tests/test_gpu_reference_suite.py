@@ -1,0 +1,43 @@
+"""The reference's OWN acceptance tests against the real kernels:
+pymbar/tests/test_mbar_solvers.py::test_solvers (:25-41) and pymbar/tests/test_mbar.py run unmodified with
+`pymbar_b200.install()` active, i.e. real `pymbar.MBAR` x real libmbar_b200.so on the B200.
+
+The unmodified reference package travels as oracle/_ref/pymbar_ref.zip (git-ignored, created by
+oracle/vendor_reference.py in the build container); where it is absent the test skips.  The full pytest log is
+kept in gpurun_out/ref_suite_gpu.log (copied to profiles/ by hand for the record)."""
+import os
+import subprocess
+import sys
+import zipfile
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ZIP = os.path.join(ROOT, "oracle", "_ref", "pymbar_ref.zip")
+
+
+@pytest.mark.skipif(not os.path.exists(ZIP), reason="oracle/_ref/pymbar_ref.zip not vendored")
+def test_reference_acceptance_suite_on_the_gpu_backend(tmp_path):
+    with zipfile.ZipFile(ZIP) as z:
+        z.extractall(tmp_path)
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([ROOT, os.path.join(ROOT, "oracle", "ref_shim"), str(tmp_path)])
+    env["PYMBAR_DISABLE_JAX"] = "1"
+    cmd = [sys.executable, "-m", "pytest", "-q", "-p", "tests._gpu_backend_plugin", "-p", "no:cacheprovider",
+           "-W", "ignore::pytest.PytestUnknownMarkWarning",
+           str(tmp_path / "pymbar" / "tests" / "test_mbar_solvers.py"),
+           str(tmp_path / "pymbar" / "tests" / "test_mbar.py")]
+    out = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=3000)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "ref_suite_gpu.log"), "w") as fh:
+        fh.write(out.stdout[-200000:])
+        fh.write("\n--- stderr ---\n" + out.stderr[-20000:])
+    lines = [ln for ln in out.stdout.strip().splitlines() if ln.strip()]
+    summary = [ln for ln in lines if " passed" in ln or " failed" in ln]
+    assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-2000:]
+    assert summary and " failed" not in summary[-1] and " error" not in summary[-1], summary
+    backend = [ln for ln in lines if ln.startswith("pymbar_b200 backend:")]
+    assert backend and "libmbar_b200.so" in backend[-1], backend
+    n_solve = int(backend[-1].split("calls=")[1].split()[0])
+    assert n_solve > 50, backend[-1]     # every MBAR() of the suite went through the GPU solve
