@@ -129,6 +129,11 @@ int mbar_b200_download_u_kn(mbar_b200_ctx* ctx, int64_t n0, int64_t n, double* u
  * With a communicator the outputs are the all-reduced global sums. */
 int mbar_b200_pass(mbar_b200_ctx* ctx, const double* f_k, double* S, double* sumL, double* G);
 
+/* The same pass at M (1 or 2) candidate vectors f[m][K] in one call, one host synchronisation: what adaptive()
+ * needs to compare its self-consistent and Newton-Raphson candidates (mbar_solvers.py:590-607 evaluates
+ * mbar_gradient at both).  S is [M][K], sumL is [M]; either may be NULL. */
+int mbar_b200_pass_multi(mbar_b200_ctx* ctx, int32_t M, const double* f, double* S, double* sumL);
+
 /* self_consistent_update(u_kn, N_k, f_k)  — mbar_solvers.py:206-257, Eq. C3, ALL states. */
 int mbar_b200_self_consistent_update(mbar_b200_ctx* ctx, const double* f_k, double* f_out);
 /* mbar_gradient — mbar_solvers.py:260-292, Eq. C6.  Unsampled states get 0 (-N_k * ...). */
@@ -159,12 +164,31 @@ int mbar_b200_solve_sci(mbar_b200_ctx* ctx, double* f_inout, double tol, int32_t
  * f_inout covers all K states; unsampled states are carried through untouched. */
 int mbar_b200_solve_adaptive(mbar_b200_ctx* ctx, double* f_inout, double tol, int32_t maxiter,
                              int32_t min_sc_iter, double gamma, mbar_b200_solve_result* result);
+/* How the two solvers above iterate.  mode 0 (default): device resident — every quantity of an iteration
+ * (gradient, candidates, K x K Cholesky of the Newton system, step choice mbar_solvers.py:607, convergence test
+ * :627-640) stays on the GPU, `batch` iterations are enqueued between two polls of a small state struct and
+ * kernels of iterations past convergence exit immediately; jax_core_adaptive (mbar_solvers.py:670-694) is the
+ * reference's counterpart of that single fused step.  mode 1: host-stepped (one round trip per pass), which is
+ * also what mode 0 falls back to when the fast kernels cannot represent an iterate.  batch < 1 keeps the
+ * current batch size. */
+int mbar_b200_set_loop_mode(mbar_b200_ctx* ctx, int32_t mode, int32_t batch);
+/* Host synchronisations spent polling the device-resident loops since creation, current mode and batch. */
+int mbar_b200_get_loop_stats(const mbar_b200_ctx* ctx, int64_t* polls, int32_t* mode, int32_t* batch);
 /* Run exactly `iters` self-consistent passes back to back with no host round trip (bench). */
 int mbar_b200_sci_iterate(mbar_b200_ctx* ctx, double* f_inout, int32_t iters);
 
 /* CUDA-event timing of the last mbar_b200_sci_iterate on the context's stream: whole loop (pass +
  * all-reduce + K-vector epilogue per iteration) and the sum of the pass-kernel launch durations. */
 int mbar_b200_last_loop_ms(mbar_b200_ctx* ctx, double* total_ms, double* kernel_ms_sum, int32_t* iters);
+
+/* ---- introspection for the benchmark ---------------------------------------------------------- */
+/* Human-readable description of the pass-kernel / Hessian-kernel variants launched last (buffers of `len`). */
+int mbar_b200_last_kernels(const mbar_b200_ctx* ctx, char* pass_kernel, char* hessian_kernel, int32_t len);
+/* CUDA-event durations of the last Hessian evaluation: weight materialisation and DMMA kernel + reduction. */
+int mbar_b200_last_hessian_ms(mbar_b200_ctx* ctx, double* weights_ms, double* hessian_ms);
+/* fp64 ceilings of this GPU measured in place (register-only DMMA.8x8x4 and DFMA loops), in TFLOP/s: the
+ * roofline denominator of mbar_b200_hessian (MEASURED_PEAKS.json has no fp64 figure). */
+int mbar_b200_measure_fp64_peak(int device, double* dmma_tflops, double* dfma_tflops);
 
 /* ---- one-shot, host-buffer entry (what a binding without residency would call) --------------- */
 /* self_consistent_update on host buffers: upload u_kn, one pass, f_out — copies inside the call. */
@@ -186,6 +210,8 @@ int mbar_b200_comm_destroy(mbar_b200_ctx* ctx);
  * and applies the K-vector update — no NCCL call and no second launch on the iteration's critical path. */
 #define MBAR_B200_IPC_HANDLE_BYTES 64
 int mbar_b200_peer_export(mbar_b200_ctx* ctx, void* handle_out /* [64] */);
+/* (needs mbar_b200_comm_init first: every host-stepped path and the K x K Hessian reduce through the communicator;
+ * at most 16 ranks) */
 int mbar_b200_peer_attach(mbar_b200_ctx* ctx, int32_t nranks, int32_t rank, const void* handles /* [nranks][64] */);
 
 #if defined(__GNUC__)

@@ -57,6 +57,7 @@ SIGNATURES = {
     "mbar_b200_set_sample_weights": (C.c_int, [_ctx, C.c_void_p]),
     "mbar_b200_download_u_kn": (C.c_int, [_ctx, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),
     "mbar_b200_pass": (C.c_int, [_ctx, _dp, _dp, _dp, _dp]),
+    "mbar_b200_pass_multi": (C.c_int, [_ctx, C.c_int32, _dp, _dp, _dp]),
     "mbar_b200_self_consistent_update": (C.c_int, [_ctx, _dp, _dp]),
     "mbar_b200_gradient": (C.c_int, [_ctx, _dp, _dp]),
     "mbar_b200_objective_and_gradient": (C.c_int, [_ctx, _dp, _dp, _dp]),
@@ -67,6 +68,11 @@ SIGNATURES = {
     "mbar_b200_solve_sci": (C.c_int, [_ctx, _dp, C.c_double, C.c_int32, C.POINTER(SolveResult)]),
     "mbar_b200_solve_adaptive": (C.c_int, [_ctx, _dp, C.c_double, C.c_int32, C.c_int32, C.c_double,
                                            C.POINTER(SolveResult)]),
+    "mbar_b200_set_loop_mode": (C.c_int, [_ctx, C.c_int32, C.c_int32]),
+    "mbar_b200_get_loop_stats": (C.c_int, [_ctx, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "mbar_b200_last_kernels": (C.c_int, [_ctx, C.c_char_p, C.c_char_p, C.c_int32]),
+    "mbar_b200_last_hessian_ms": (C.c_int, [_ctx, _dp, _dp]),
+    "mbar_b200_measure_fp64_peak": (C.c_int, [C.c_int, _dp, _dp]),
     "mbar_b200_sci_iterate": (C.c_int, [_ctx, _dp, C.c_int32]),
     "mbar_b200_last_loop_ms": (C.c_int, [_ctx, _dp, _dp, C.POINTER(C.c_int32)]),
     "mbar_b200_self_consistent_update_host": (C.c_int, [C.c_int, C.c_int32, C.c_int64, C.c_void_p, C.c_int64,

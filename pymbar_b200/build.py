@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmbar_b200.so")
-SOURCES = ["ctx.cu", "pass_generic.cu", "pass_fused.cu", "hessian.cu", "logw.cu", "api.cu"]
+SOURCES = ["ctx.cu", "pass_generic.cu", "pass_fused.cu", "hessian.cu", "logw.cu", "api.cu", "loops.cu", "ubench.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--use_fast_math=false",

@@ -107,14 +107,8 @@ __global__ void sci_epilogue_kernel(const double* __restrict__ out, double* __re
 // ------------------------------------------------------------------------------------------
 // one streaming pass
 // ------------------------------------------------------------------------------------------
-struct PassWant {
-    bool L = false;          // keep per-sample L'_n on the device
-    bool unsampled = false;  // need log-domain sums for N_k == 0 states
-    bool G = false;          // K x K second moments
-    bool Gall = false;       // ... including the unsampled states' rows and columns
-};
-
-static int check_range(mbar_b200_ctx* c, const double* f) {
+namespace mbar {
+int check_range(mbar_b200_ctx* c, const double* f) {
     for (int k : c->active) {
         const double ck = f[k] + c->h_logNk[k];
         MBAR_REQUIRE(std::isfinite(ck) && std::fabs(ck) < C_RANGE, MBAR_B200_ERR_RANGE,
@@ -124,11 +118,16 @@ static int check_range(mbar_b200_ctx* c, const double* f) {
 }
 
 // Runs the pass, all-reduces, downloads the packed result into ctx->h_out.
-static int run_pass(mbar_b200_ctx* c, const double* f, PassWant want) {
+int run_pass(mbar_b200_ctx* c, const double* f, PassWant want) {
     MBAR_REQUIRE(c && f, MBAR_B200_ERR_INVALID, "NULL argument");
     MBAR_REQUIRE(c->ready, MBAR_B200_ERR_NOT_READY, "u_kn has not been uploaded");
+    // a sharded problem needs a working reduction: peers attached without a communicator would silently
+    // return shard-local sums from every host-stepped path
+    MBAR_REQUIRE(c->nranks == 1 || c->comm, MBAR_B200_ERR_NOT_READY,
+                 "sharded problem (%d ranks) without a communicator: call mbar_b200_comm_init", c->nranks);
     MBAR_CUDA(cudaSetDevice(c->device));
     MBAR_TRY(check_range(c, f));
+    NvtxRange nvtx_("mbar_b200::pass");
     const int K = c->K;
     const PassLayout lay{K};
     const bool needUnsampled = want.unsampled && (int)c->active.size() < K;
@@ -193,6 +192,7 @@ static int run_pass(mbar_b200_ctx* c, const double* f, PassWant want) {
         if (attempt == 0) ++attempt;   // skip the linear generic pass: it would underflow the same way
     }
     if (want.G || want.Gall) {
+        NvtxRange nvtxH("mbar_b200::hessian");
         MBAR_TRY(launch_hessian(c, f, want.Gall));
         MBAR_TRY(comm_allreduce(c, c->d_out + lay.G(), K * K, 0));
         MBAR_CUDA(cudaMemcpyAsync(c->h_out + lay.G(), c->d_out + lay.G(), (size_t)K * K * sizeof(double),
@@ -203,7 +203,7 @@ static int run_pass(mbar_b200_ctx* c, const double* f, PassWant want) {
     return MBAR_B200_OK;
 }
 
-static double global_sumx(mbar_b200_ctx* c, int* rc) {
+double global_sumx(mbar_b200_ctx* c, int* rc) {
     *rc = MBAR_B200_OK;
     const double mine = c->d_wgt ? c->sumXw : c->sumX;
     if (!c->comm || c->nranks == 1) return mine;
@@ -216,8 +216,10 @@ static double global_sumx(mbar_b200_ctx* c, int* rc) {
     return v;
 }
 
+}  // namespace mbar
+
 // ------------------------------------------------------------------------------------------
-// small dense helpers for the Newton step (host, K x K)
+// small dense helpers for the Newton step (host-stepped fallback loop, K x K)
 // ------------------------------------------------------------------------------------------
 // In-place Cholesky of the n x n SPD matrix A (row-major, lower); returns false if not PD.
 static bool cholesky(std::vector<double>& A, int n) {
@@ -274,6 +276,92 @@ int mbar_b200_pass(mbar_b200_ctx* c, const double* f, double* S, double* sumL, d
                 G[(size_t)i * K + j] = d > 0 ? Gh[(size_t)i * K + j] / d : 0.0;
             }
     }
+    return MBAR_B200_OK;
+}
+
+// M candidate f-vectors in one call (SURVEY.md 8b `mbar_pass(ctx, M, f[M][K], ...)`): the launches are
+// enqueued back to back on the fused kernel and synchronised ONCE; anything the fused kernel cannot take
+// falls back to the robust single-candidate path.
+int mbar_b200_pass_multi(mbar_b200_ctx* c, int32_t M, const double* f, double* S, double* sumL) {
+    MBAR_REQUIRE(c && f, MBAR_B200_ERR_INVALID, "NULL argument");
+    MBAR_REQUIRE(M >= 1 && M <= 2, MBAR_B200_ERR_INVALID, "M=%d: 1 or 2 candidates", M);
+    MBAR_REQUIRE(c->ready, MBAR_B200_ERR_NOT_READY, "u_kn has not been uploaded");
+    MBAR_REQUIRE(c->nranks == 1 || c->comm, MBAR_B200_ERR_NOT_READY, "sharded problem without a communicator");
+    MBAR_CUDA(cudaSetDevice(c->device));
+    const int K = c->K;
+    const PassLayout lay{K};
+    NvtxRange nvtx_("mbar_b200::pass_multi");
+    for (int m = 0; m < M; ++m) MBAR_TRY(check_range(c, f + (size_t)m * K));
+    int rc0;
+    const double sx = global_sumx(c, &rc0);
+    MBAR_TRY(rc0);
+    bool fast = c->kernelChoice != MBAR_B200_KERNEL_GENERIC;
+    FusedParams p[2];
+    for (int m = 0; m < M && fast; ++m) {
+        bool ok = false;
+        // candidate m stages its constants in its own device row / pinned row (the copies are asynchronous)
+        MBAR_TRY(fused_prepare(c, f + (size_t)m * K, false, false, &p[m], &ok,
+                               m == 0 ? c->d_c : c->d_av + 4 * (size_t)K, m == 0 ? c->h_f : c->h_f + 6 * (size_t)K));
+        p[m].out = c->d_outM + (size_t)m * lay.size(false);
+        fast = ok;
+    }
+    if (fast) {
+        for (int m = 0; m < M; ++m) {
+            MBAR_TRY(fused_enqueue(c, p[m]));
+            MBAR_TRY(comm_allreduce(c, p[m].out, K + 2, 0));
+        }
+        MBAR_CUDA(cudaMemcpyAsync(c->h_out, c->d_outM, (size_t)M * lay.size(false) * sizeof(double),
+                                  cudaMemcpyDeviceToHost, c->stream));
+        MBAR_CUDA(cudaStreamSynchronize(c->stream));
+        c->d2hBytes += (int64_t)M * lay.size(false) * 8;
+        for (int m = 0; m < M && fast; ++m) {
+            const double* o = c->h_out + (size_t)m * lay.size(false);
+            if (o[lay.flag()] != 0.0) fast = false;
+            for (int k : c->active)
+                if (!(o[k] > 1e-280)) fast = false;
+        }
+        if (fast) {
+            for (int m = 0; m < M; ++m) {
+                const double* o = c->h_out + (size_t)m * lay.size(false);
+                if (S)
+                    for (int k = 0; k < K; ++k) S[(size_t)m * K + k] = c->h_Nk[k] > 0 ? o[k] : 0.0;
+                if (sumL) sumL[m] = o[lay.sumL()] - sx;
+            }
+            return MBAR_B200_OK;
+        }
+    }
+    for (int m = 0; m < M; ++m) {
+        MBAR_TRY(run_pass(c, f + (size_t)m * K, PassWant{}));
+        if (S) std::memcpy(S + (size_t)m * K, c->h_out + lay.S(), K * sizeof(double));
+        if (sumL) sumL[m] = c->h_out[lay.sumL()] - sx;
+    }
+    return MBAR_B200_OK;
+}
+
+int mbar_b200_last_kernels(const mbar_b200_ctx* c, char* pass_kernel, char* hessian_kernel, int32_t len) {
+    MBAR_REQUIRE(c && len > 0, MBAR_B200_ERR_INVALID, "bad argument");
+    if (pass_kernel) snprintf(pass_kernel, (size_t)len, "%s", c->lastKernel);
+    if (hessian_kernel) snprintf(hessian_kernel, (size_t)len, "%s", c->lastHessKernel);
+    return MBAR_B200_OK;
+}
+
+int mbar_b200_last_hessian_ms(mbar_b200_ctx* c, double* weights_ms, double* hessian_ms) {
+    MBAR_REQUIRE(c, MBAR_B200_ERR_INVALID, "ctx is NULL");
+    MBAR_CUDA(cudaSetDevice(c->device));
+    MBAR_CUDA(cudaStreamSynchronize(c->stream));
+    float a = 0.f, b = 0.f;
+    if (cudaEventElapsedTime(&a, c->evH0, c->evH1) != cudaSuccess) { cudaGetLastError(); a = 0.f; }
+    if (cudaEventElapsedTime(&b, c->evH1, c->evH2) != cudaSuccess) { cudaGetLastError(); b = 0.f; }
+    if (weights_ms) *weights_ms = a;
+    if (hessian_ms) *hessian_ms = b;
+    return MBAR_B200_OK;
+}
+
+int mbar_b200_get_loop_stats(const mbar_b200_ctx* c, int64_t* polls, int32_t* mode, int32_t* batch) {
+    MBAR_REQUIRE(c, MBAR_B200_ERR_INVALID, "ctx is NULL");
+    if (polls) *polls = c->loopPolls;
+    if (mode) *mode = c->loopMode;
+    if (batch) *batch = c->loopBatch;
     return MBAR_B200_OK;
 }
 
@@ -391,8 +479,13 @@ static double rel_delta(const mbar_b200_ctx* c, const std::vector<double>& fn, c
     return md;
 }
 
-int mbar_b200_solve_sci(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter,
-                        mbar_b200_solve_result* res) {
+}  // extern "C"
+
+namespace mbar {
+// Host-stepped loops (round 1): one host round trip per pass.  They are the robust fallback of the
+// device-resident loops in loops.cu (generic kernel, log-domain sums, ridge retries) and stay selectable with
+// mbar_b200_set_loop_mode(ctx, 1).
+int solve_sci_stepped(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter, mbar_b200_solve_result* res) {
     MBAR_REQUIRE(c && f, MBAR_B200_ERR_INVALID, "NULL argument");
     const int K = c->K;
     const PassLayout lay{K};
@@ -442,8 +535,8 @@ int mbar_b200_solve_sci(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter
     return rc;
 }
 
-int mbar_b200_solve_adaptive(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter,
-                             int32_t min_sc_iter, double gamma, mbar_b200_solve_result* res) {
+int solve_adaptive_stepped(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter, int32_t min_sc_iter,
+                           double gamma, mbar_b200_solve_result* res) {
     MBAR_REQUIRE(c && f, MBAR_B200_ERR_INVALID, "NULL argument");
     const int K = c->K;
     const PassLayout lay{K};
@@ -490,7 +583,7 @@ int mbar_b200_solve_adaptive(mbar_b200_ctx* c, double* f, double tol, int32_t ma
         if (na > 1) {
             const int n = na - 1;
             const double* Gh = c->h_out + lay.G();
-            double ridge = 0.0, tr = 0.0;
+            double ridge = 0.0, ridgeRel = 0.0, tr = 0.0;
             for (int a = 1; a < na; ++a) {
                 const int i = c->active[a];
                 tr += c->h_Nk[i] * c->h_out[i];
@@ -517,7 +610,8 @@ int mbar_b200_solve_adaptive(mbar_b200_ctx* c, double* f, double tol, int32_t ma
                         if (!std::isfinite(f_nr[c->active[a]]) || std::fabs(f_nr[c->active[a]]) > 0.5 * C_RANGE)
                             haveNr = false;
                 } else {
-                    ridge = (ridge == 0.0 ? 1e-12 : ridge * 1e3) * (tr / n + 1e-300);
+                    ridgeRel = (ridgeRel == 0.0) ? 1e-12 : ridgeRel * 1e3;   // relative to the mean diagonal
+                    ridge = ridgeRel * (tr / n + 1e-300);
                 }
             }
         }
@@ -574,6 +668,33 @@ int mbar_b200_solve_adaptive(mbar_b200_ctx* c, double* f, double tol, int32_t ma
     return rc;
 }
 
+}  // namespace mbar
+
+extern "C" {
+
+int mbar_b200_solve_sci(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter, mbar_b200_solve_result* res) {
+    MBAR_REQUIRE(c && f, MBAR_B200_ERR_INVALID, "NULL argument");
+    NvtxRange nvtx_("mbar_b200::solve_sci");
+    if (c->loopMode == 1) return solve_sci_stepped(c, f, tol, maxiter, res);
+    return solve_sci_device(c, f, tol, maxiter, res);
+}
+
+int mbar_b200_solve_adaptive(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter, int32_t min_sc_iter,
+                             double gamma, mbar_b200_solve_result* res) {
+    MBAR_REQUIRE(c && f, MBAR_B200_ERR_INVALID, "NULL argument");
+    NvtxRange nvtx_("mbar_b200::solve_adaptive");
+    if (c->loopMode == 1) return solve_adaptive_stepped(c, f, tol, maxiter, min_sc_iter, gamma, res);
+    return solve_adaptive_device(c, f, tol, maxiter, min_sc_iter, gamma, res);
+}
+
+int mbar_b200_set_loop_mode(mbar_b200_ctx* c, int32_t mode, int32_t batch) {
+    MBAR_REQUIRE(c, MBAR_B200_ERR_INVALID, "ctx is NULL");
+    MBAR_REQUIRE(mode == 0 || mode == 1, MBAR_B200_ERR_INVALID, "mode=%d (0 device-resident, 1 host-stepped)", mode);
+    c->loopMode = mode;
+    if (batch >= 1) c->loopBatch = batch > 64 ? 64 : batch;
+    return MBAR_B200_OK;
+}
+
 int mbar_b200_sci_iterate(mbar_b200_ctx* c, double* f, int32_t iters) {
     MBAR_REQUIRE(c && f && iters >= 0, MBAR_B200_ERR_INVALID, "bad argument");
     MBAR_REQUIRE(c->ready, MBAR_B200_ERR_NOT_READY, "u_kn has not been uploaded");
@@ -613,6 +734,10 @@ int mbar_b200_sci_iterate(mbar_b200_ctx* c, double* f, int32_t iters) {
     // One kernel per iteration when the exchange can live inside the pass kernel (single GPU, or peers
     // attached through mbar_b200_peer_attach); otherwise pass -> ncclAllReduce -> epilogue kernel.
     const bool inKernel = (c->nranks == 1 || c->peerReady) && !std::getenv("MBAR_B200_NO_FUSED_EPILOGUE");
+    MBAR_REQUIRE(c->nranks == 1 || c->comm, MBAR_B200_ERR_NOT_READY,
+                 "sharded problem (%d ranks) without a communicator: call mbar_b200_comm_init", c->nranks);
+    if (inKernel && c->peerReady) MBAR_TRY(comm_rendezvous(c));
+    NvtxRange nvtx_("mbar_b200::sci_iterate");
     if (inKernel) {
         p.epi = 1;
         p.f = c->d_f;
@@ -622,7 +747,6 @@ int mbar_b200_sci_iterate(mbar_b200_ctx* c, double* f, int32_t iters) {
     }
     for (int it = 0; it < iters; ++it) {
         if (perLaunch) MBAR_CUDA(cudaEventRecord(ev[2 * it], c->stream));
-        p.seq = ++c->peerSeq;
         MBAR_TRY(fused_enqueue(c, p));
         if (perLaunch) MBAR_CUDA(cudaEventRecord(ev[2 * it + 1], c->stream));
         if (!inKernel) {
@@ -738,13 +862,13 @@ int mbar_b200_comm_init(mbar_b200_ctx* c, int32_t nranks, int32_t rank, const vo
     return MBAR_B200_OK;
 }
 
-static size_t inbox_doubles(int K) { return (size_t)2 * 8 * (K + 2); }
+static size_t inbox_doubles(int K) { return (size_t)2 * MAX_PEERS * (K + 2); }
 
 int mbar_b200_peer_export(mbar_b200_ctx* c, void* handle_out) {
     MBAR_REQUIRE(c && handle_out, MBAR_B200_ERR_INVALID, "NULL argument");
     MBAR_CUDA(cudaSetDevice(c->device));
     if (!c->d_inbox) {
-        const size_t bytes = inbox_doubles(c->K) * sizeof(double) + 2 * 8 * sizeof(unsigned long long);
+        const size_t bytes = inbox_doubles(c->K) * sizeof(double) + 2 * MAX_PEERS * sizeof(unsigned long long);
         MBAR_CUDA(cudaMalloc((void**)&c->d_inbox, bytes));
         MBAR_CUDA(cudaMemset(c->d_inbox, 0, bytes));
     }
@@ -757,9 +881,14 @@ int mbar_b200_peer_export(mbar_b200_ctx* c, void* handle_out) {
 
 int mbar_b200_peer_attach(mbar_b200_ctx* c, int32_t nranks, int32_t rank, const void* handles) {
     MBAR_REQUIRE(c && handles, MBAR_B200_ERR_INVALID, "NULL argument");
-    MBAR_REQUIRE(nranks >= 1 && nranks <= 8 && rank >= 0 && rank < nranks, MBAR_B200_ERR_INVALID,
-                 "rank %d of %d (at most 8 peers)", rank, nranks);
+    MBAR_REQUIRE(nranks >= 1 && nranks <= MAX_PEERS && rank >= 0 && rank < nranks, MBAR_B200_ERR_INVALID,
+                 "rank %d of %d (at most %d peers)", rank, nranks, MAX_PEERS);
     MBAR_REQUIRE(c->d_inbox, MBAR_B200_ERR_NOT_READY, "call mbar_b200_peer_export first");
+    // The peer inbox only carries the exchange of the device-resident loops; every host-stepped path (and the
+    // K x K Hessian) reduces through the communicator, so a sharded problem without one would return
+    // shard-local sums.  Require it instead of guessing.
+    MBAR_REQUIRE(nranks == 1 || (c->comm && c->nranks == nranks && c->rank == rank), MBAR_B200_ERR_NOT_READY,
+                 "mbar_b200_peer_attach needs mbar_b200_comm_init(nranks=%d, rank=%d) first", nranks, rank);
     MBAR_CUDA(cudaSetDevice(c->device));
     c->peer = PeerCfg{};
     c->peer.nranks = nranks;
@@ -775,11 +904,9 @@ int mbar_b200_peer_attach(mbar_b200_ctx* c, int32_t nranks, int32_t rank, const 
         c->peer.inbox[q] = static_cast<double*>(ptr);
         c->peer.flags[q] = reinterpret_cast<unsigned long long*>(static_cast<double*>(ptr) + inbox_doubles(c->K));
     }
+    c->peer.seq = c->d_seq;
+    MBAR_CUDA(cudaMemset(c->d_seq, 0, sizeof(unsigned long long)));
     c->peerReady = nranks > 1;
-    if (c->nranks == 1) {           // peers without an NCCL communicator: still a sharded problem
-        c->nranks = nranks;
-        c->rank = rank;
-    }
     return MBAR_B200_OK;
 }
 

@@ -455,7 +455,20 @@ int mbar_b200_create(mbar_b200_ctx** out, int device, int32_t K, int64_t N_local
     ALLOC(c->d_flag, 4 * sizeof(int));
     ALLOC(c->d_f, 8 * (size_t)K * sizeof(double));
     ALLOC(c->d_scratch, ((size_t)K * K + 4 * (size_t)K + 1024) * sizeof(double));
+    ALLOC(c->d_loop, sizeof(mbar::LoopState));
+    ALLOC(c->d_av, 8 * (size_t)K * sizeof(double));
+    ALLOC(c->d_outM, 2 * (size_t)lay.size(false) * sizeof(double));
+    ALLOC(c->d_A, (size_t)K * K * sizeof(double));
+    ALLOC(c->d_active, (size_t)K * sizeof(int));
+    ALLOC(c->d_seq, sizeof(unsigned long long));
 #undef ALLOC
+    MBAR_CUDA(cudaHostAlloc((void**)&c->h_loop, sizeof(mbar::LoopState), cudaHostAllocDefault));
+    MBAR_CUDA(cudaMemset(c->d_loop, 0, sizeof(mbar::LoopState)));
+    MBAR_CUDA(cudaMemset(c->d_seq, 0, sizeof(unsigned long long)));
+    MBAR_CUDA(cudaMemcpy(c->d_active, c->active.data(), c->active.size() * sizeof(int), cudaMemcpyHostToDevice));
+    MBAR_CUDA(cudaEventCreate(&c->evH0));
+    MBAR_CUDA(cudaEventCreate(&c->evH1));
+    MBAR_CUDA(cudaEventCreate(&c->evH2));
     MBAR_CUDA(cudaHostAlloc((void**)&c->h_out, (size_t)lay.size(true) * sizeof(double), cudaHostAllocDefault));
     MBAR_CUDA(cudaHostAlloc((void**)&c->h_f, 8 * (size_t)K * sizeof(double), cudaHostAllocDefault));
     MBAR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -509,6 +522,12 @@ int mbar_b200_destroy(mbar_b200_ctx* c) {
     cudaFree(c->d_rowmask); cudaFree(c->d_zeromask); cudaFree(c->d_onesmask); cudaFree(c->d_partial); cudaFree(c->d_out); cudaFree(c->d_L);
     cudaFree(c->d_W); cudaFree(c->d_ticket); cudaFree(c->d_flag); cudaFree(c->d_f);
     cudaFree(c->d_scratch);
+    cudaFree(c->d_loop); cudaFree(c->d_av); cudaFree(c->d_outM); cudaFree(c->d_A); cudaFree(c->d_active);
+    cudaFree(c->d_seq); cudaFree(c->d_Wt);
+    if (c->h_loop) cudaFreeHost(c->h_loop);
+    if (c->evH0) cudaEventDestroy(c->evH0);
+    if (c->evH1) cudaEventDestroy(c->evH1);
+    if (c->evH2) cudaEventDestroy(c->evH2);
     for (int i = 0; i < 2; ++i) {
         if (c->stage_pinned[i]) cudaFreeHost(c->stage_pinned[i]);
         cudaFree(c->stage_dev[i]);

@@ -57,10 +57,31 @@ struct PassLayout {
 };
 
 // Peer-memory exchange of the per-pass partial sums (fused into the pass kernel's last CTA).
+constexpr int MAX_PEERS = 16;
 struct PeerCfg {
     int nranks = 1, rank = 0;
-    double* inbox[8] = {nullptr};               // inbox[q]: rank q's [2][nranks][K+2] buffer, mapped here
-    unsigned long long* flags[8] = {nullptr};   // flags[q]: rank q's [2][nranks] sequence numbers
+    double* inbox[MAX_PEERS] = {nullptr};               // inbox[q]: rank q's [2][nranks][K+2] buffer, mapped here
+    unsigned long long* flags[MAX_PEERS] = {nullptr};   // flags[q]: rank q's [2][nranks] sequence numbers
+    // Exchange sequence number, kept on the DEVICE and advanced by the last CTA of every launch that
+    // actually runs: launches that exit early (solver already converged) must not consume a number, or two
+    // executed launches could reuse an inbox parity without an exchange in between.
+    unsigned long long* seq = nullptr;
+};
+
+// State of a device-resident solver loop (device memory + pinned host mirror).  Every kernel of an iteration
+// starts with `if (loop->done) return;`, so the host can enqueue a batch of iterations without knowing when
+// the solver converges and polls this struct once per batch: no per-iteration host round trip.
+struct LoopState {
+    int done;            // 1: stop (converged, failed or maxiter reached)
+    int status;          // 0 ok | 1 range/underflow problem: redo on the robust host-stepped path | 2 comm
+    int success;         // convergence criterion met (mbar_solvers.py:627-640)
+    int iterations, nr_iterations, sci_iterations;
+    int maxiter, min_sc_iter;
+    int haveNr;          // this iteration has a valid Newton candidate
+    int cholFail;        // last Cholesky attempt met a non-positive pivot
+    double tol, gamma;
+    double max_delta, max_diff, gnorm;
+    double gn_sci, gn_nr;
 };
 
 }  // namespace mbar
@@ -100,7 +121,7 @@ struct mbar_b200_ctx {
     double* d_out = nullptr;        // PassLayout packed result (with G)
     double* h_out = nullptr;        // pinned mirror of d_out
     double* d_L = nullptr;          // [nTiles*32] per-sample L_n (lazy)
-    double* d_W = nullptr;          // reserved
+    double* d_W = nullptr;          // per-CTA partial blocks of the Hessian kernels (gpartBytes)
     unsigned int* d_ticket = nullptr;
     int* d_flag = nullptr;          // [4] error/diagnostic flags
     double* d_f = nullptr;          // [4][K] device-resident f vectors for native loops
@@ -118,12 +139,29 @@ struct mbar_b200_ctx {
     double* d_inbox = nullptr;
     mbar::PeerCfg peer;
     bool peerReady = false;
-    unsigned long long peerSeq = 0;
     std::vector<void*> peerMapped;
 
     // communicator (NCCL, dlopen'd)
     void* comm = nullptr;
     int nranks = 1, rank = 0;
+
+    // device-resident solver loops
+    mbar::LoopState* d_loop = nullptr;   // device
+    mbar::LoopState* h_loop = nullptr;   // pinned mirror
+    double* d_av = nullptr;              // [8][K] adaptive work vectors (f_sci, f_nr, g, c_sci, c_nr, c_hess, x, -)
+    double* d_outM = nullptr;            // [2][2K+2] pass outputs of the two candidates
+    double* d_A = nullptr;               // [K*K] Newton matrix / Cholesky factor
+    int* d_active = nullptr;             // [K] indices of the sampled states
+    unsigned long long* d_seq = nullptr; // peer-exchange sequence number (device-side, see PeerCfg::seq)
+    int loopMode = 0;                    // 0 device-resident, 1 host-stepped (round-1 behaviour)
+    int loopBatch = 4;                   // iterations enqueued between two polls of LoopState
+    int64_t loopPolls = 0;               // host synchronisations spent polling LoopState
+    double* d_Wt = nullptr;              // [nTiles][K][32] materialised N_k W_nk (swizzled) for the Hessian
+    size_t gpartBytes = 0;               // size of d_W (per-CTA partial blocks of the Hessian kernels)
+    char lastKernel[200] = "";           // description of the pass-kernel variant launched last
+    char lastHessKernel[200] = "";       // ... and of the Hessian kernel path
+    double lastHessMs = 0.0, lastWeightsMs = 0.0;
+    cudaEvent_t evH0 = nullptr, evH1 = nullptr, evH2 = nullptr;
 
     // counters
     int64_t launches = 0, passes = 0, h2dBytes = 0, d2hBytes = 0;
@@ -149,7 +187,7 @@ struct FusedParams {
     double* f;                             // [K] device f_k (epilogue) or NULL
     double* cnext;                         // [K] where the epilogue writes c for the next launch
     PeerCfg peer;
-    unsigned long long seq;                // exchange sequence number (>= 1)
+    LoopState* loop;                       // device-resident loop state (early exit + convergence) or NULL
     int epi, first;
     int64_t N, nTiles, nStages;
     double mid;
@@ -157,15 +195,46 @@ struct FusedParams {
     uint32_t tileBytes, stageBytes;
 };
 
+// What a host-driven pass should leave behind (api.cu: run_pass).
+struct PassWant {
+    bool L = false;          // keep per-sample L'_n on the device
+    bool unsampled = false;  // need log-domain sums for N_k == 0 states
+    bool G = false;          // K x K second moments
+    bool Gall = false;       // ... including the unsampled states' rows and columns
+};
+
+// NVTX ranges around pass / exchange / Hessian / upload / solver loops.  nvtx3 is header
+// only: without an attached tool every call is a no-op through a NULL function table.
+struct NvtxRange {
+    explicit NvtxRange(const char* name);
+    ~NvtxRange();
+};
+
 // ---- host-side helpers implemented across the .cu files ----
+int check_range(mbar_b200_ctx* c, const double* f);
+int run_pass(mbar_b200_ctx* c, const double* f, PassWant want);   // pass + all-reduce + D2H into ctx->h_out
+double global_sumx(mbar_b200_ctx* c, int* rc);
+int solve_sci_stepped(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter, mbar_b200_solve_result* res);
+int solve_adaptive_stepped(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter, int32_t min_sc_iter,
+                           double gamma, mbar_b200_solve_result* res);
+int solve_sci_device(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter, mbar_b200_solve_result* res);
+int solve_adaptive_device(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter, int32_t min_sc_iter,
+                          double gamma, mbar_b200_solve_result* res);
+// stream-ordered rendezvous of all ranks (one tiny all-reduce) before the first in-kernel peer exchange of a loop
+int comm_rendezvous(mbar_b200_ctx* ctx);
 int retile_chunk(mbar_b200_ctx* ctx, const double* d_rowmajor, int64_t ldCols, int64_t tile0,
                  int64_t nTilesChunk, int64_t validCols, cudaStream_t s);
 int launch_pass_generic(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool logAll);
 int launch_pass_fused(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, bool* usedOut);
-int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, FusedParams* out, bool* ok);
+// d_cdst / h_stage: where c = f + log N - mid is staged (default: ctx->d_c / ctx->h_f); midForce: reuse the
+// centring of a previous prepare (candidates evaluated against the same exp(c) range), NaN = derive from f
+int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, FusedParams* out, bool* ok,
+                  double* d_cdst = nullptr, double* h_stage = nullptr);
 int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p);
 bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, bool allStates, double* midOut, double* spreadOut);
 int launch_hessian(mbar_b200_ctx* ctx, const double* h_f, bool allRows);
+// same with c_k = f_k + log N_k already on the device (device-resident loops); loop may be NULL
+int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, LoopState* loop);
 int launch_logw(mbar_b200_ctx* ctx, const double* h_f, double* logW_host, int64_t ld, int expo);
 int launch_synth(mbar_b200_ctx* ctx, const mbar_b200_synth* spec);
 int launch_untile(mbar_b200_ctx* ctx, int64_t n0, int64_t n, double* d_dst, int64_t ld);

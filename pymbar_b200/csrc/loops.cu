@@ -1,0 +1,641 @@
+// Device-resident solver loops: no host round trip between iterations.
+//
+// Reference loops being replaced: adaptive() (mbar_solvers.py:510-667; one iteration = mbar_solvers.py:575-640,
+// the JAX build runs that iteration as ONE jitted step, jax_core_adaptive :670-694) and the plain
+// self-consistent iteration (Eq. C3).  Round 1 stepped these loops from the host: after every pass a
+// cudaStreamSynchronize, a D2H copy, a K-vector update on the CPU, and for Newton a D2H of K^2 doubles plus a
+// single-threaded host Cholesky.  At the sizes of BASELINE configs C2 / C4 (a pass takes 30-100 us) the loop was
+// round-trip-bound.
+//
+// Here every quantity of an iteration lives on the device:
+//   self-consistent:  pass kernel (its last CTA exchanges the sums, updates f, tests convergence)
+//   adaptive:         pass(f) -> adapt_pre (g, f_sci) -> Hessian -> newton_build -> newton (Cholesky + solves,
+//                     f_nr) -> pass(f_sci), pass(f_nr) -> adapt_post (step choice :607, convergence :627-640)
+// Every kernel starts with `if (loop->done) return;`, so the host enqueues `loopBatch` iterations at a time and
+// reads the 96-byte LoopState once per batch.  Anything the fast path cannot represent (range flag of the fused
+// kernel, an underflowing S_k, non-finite candidates) sets status = 1 and the host finishes on the robust
+// host-stepped loop (api.cu), starting from the last good f.
+#include <nvtx3/nvToolsExt.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "internal.cuh"
+
+namespace mbar {
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
+
+// rows of ctx->d_av
+enum { AV_FSCI = 0, AV_FNR = 1, AV_G = 2, AV_CSCI = 3, AV_CNR = 4, AV_CH = 5, AV_X = 6, AV_DIAG = 7 };
+
+__device__ __forceinline__ bool loop_done(const LoopState* loop) {
+    return *reinterpret_cast<const volatile int*>(&loop->done) != 0;
+}
+__device__ __forceinline__ bool row_on(const unsigned long long* __restrict__ mask, int k) {
+    return (mask[k >> 6] >> (k & 63)) & 1ull;
+}
+
+// Deterministic block-wide reductions (fixed tree): sum and NaN-propagating max.
+__device__ double block_sum(double v, double* s_buf) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_buf[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_buf[w];
+    return t;
+}
+__device__ double block_max_nan(double v, double* s_buf) {
+    // NaN must survive (mbar_solvers.py:636 treats a NaN max_delta specially): carry it as +inf marker pairs
+    double nanflag = (v != v) ? 1.0 : 0.0;
+    if (v != v) v = 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+        v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        nanflag = fmax(nanflag, __shfl_xor_sync(0xffffffffu, nanflag, o));
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        s_buf[threadIdx.x >> 5] = v;
+        s_buf[32 + (threadIdx.x >> 5)] = nanflag;
+    }
+    __syncthreads();
+    double t = 0.0, nf = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+        t = fmax(t, s_buf[w]);
+        nf = fmax(nf, s_buf[32 + w]);
+    }
+    return nf > 0.0 ? NAN : t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// self-consistent iteration, NCCL flavour (no peer memory): epilogue kernel after the all-reduce
+// ------------------------------------------------------------------------------------------------
+// f <- f - log S (sampled states), gauge f[first] = 0, c <- f + log N - mid, convergence test.
+__global__ void __launch_bounds__(256)
+sci_loop_epilogue_kernel(const double* __restrict__ out, double* __restrict__ f, double* __restrict__ c,
+                         const double* __restrict__ Nk, const unsigned long long* __restrict__ rowmask, int K,
+                         int first, double mid, LoopState* loop) {
+    if (loop_done(loop)) return;
+    __shared__ double s_buf[64];
+    __shared__ double s_f0;
+    if (threadIdx.x == 0) s_f0 = f[first] - log(out[first]);
+    __syncthreads();
+    const double thr = fmin(1.0e-8, loop->tol);
+    double md = 0.0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        if (row_on(rowmask, k)) {
+            const double fo = f[k];
+            const double fn = (out[k] > 1e-280) ? fo - log(out[k]) - s_f0 : NAN;
+            f[k] = fn;
+            c[k] = fn + log(Nk[k]) - mid;
+            if (fn != fn) md = NAN;
+            if (k != first && md == md) {
+                double div = fabs(fn);
+                if (div < thr) div = 1.0;
+                md = fmax(md, fabs(fn - fo) / div);
+            }
+        }
+    }
+    md = block_max_nan(md, s_buf);
+    if (threadIdx.x == 0) {
+        const int it = loop->iterations + 1;
+        loop->iterations = it;
+        loop->sci_iterations = it;
+        loop->max_delta = md;
+        if (md != md || out[K + 1] != 0.0) {
+            loop->status = 1;
+            loop->done = 1;
+        } else if (md < loop->tol) {
+            loop->success = 1;
+            loop->done = 1;
+        } else if (it >= loop->maxiter) {
+            loop->done = 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// adaptive(): K-vector kernels
+// ------------------------------------------------------------------------------------------------
+// After the pass at f: gradient (Eq. C6), the self-consistent candidate (Eq. C3) with the gauge of
+// mbar_solvers.py:588, the constants of the next launches and the diagonal N_i S_i of the Hessian (Eq. C9).
+__global__ void __launch_bounds__(256)
+adapt_pre_kernel(const double* __restrict__ out, const double* __restrict__ f, const double* __restrict__ Nk,
+                 const unsigned long long* __restrict__ rowmask, int K, int first, double mid,
+                 double* __restrict__ av, LoopState* loop) {
+    if (loop_done(loop)) return;
+    __shared__ double s_buf[64];
+    __shared__ double s_f0;
+    if (threadIdx.x == 0) s_f0 = f[first] - log(out[first]);
+    __syncthreads();
+    double bad = (threadIdx.x == 0 && out[K + 1] != 0.0) ? 1.0 : 0.0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const double fk = f[k];
+        if (row_on(rowmask, k)) {
+            const double S = out[k], n = Nk[k], ln = log(n);
+            if (!(S > 1e-280) || !(S < 1e300)) bad = 1.0;
+            const double fs = fk - log(S) - s_f0;
+            av[AV_FSCI * K + k] = fs;
+            av[AV_CSCI * K + k] = fs + ln - mid;
+            av[AV_G * K + k] = n * (S - 1.0);
+            av[AV_CH * K + k] = fk + ln;
+            av[AV_DIAG * K + k] = n * S;
+        } else {
+            av[AV_FSCI * K + k] = fk;
+            av[AV_CSCI * K + k] = 0.0;
+            av[AV_G * K + k] = 0.0;
+            av[AV_CH * K + k] = 0.0;
+            av[AV_DIAG * K + k] = 0.0;
+        }
+    }
+    bad = block_sum(bad, s_buf);
+    if (threadIdx.x == 0 && bad > 0.0) {
+        loop->status = out[K + 1] >= 1.0e6 ? 2 : 1;
+        loop->done = 1;
+    }
+}
+
+// Reduced Newton matrix A = H[1:,1:] over the sampled states (gauge state dropped, mbar_solvers.py:804-818 /
+// SURVEY.md Appendix A): A_ab = delta_ab N_i S_i (1 + ridge) - Ghat_ij, stored column-major (it is symmetric).
+// ridgeRel > 0 is the retry after a failed factorisation (only then: onlyIfFail).
+__global__ void __launch_bounds__(256)
+newton_build_kernel(const double* __restrict__ G, const double* __restrict__ av, const int* __restrict__ active,
+                    int na, int K, double* __restrict__ A, double ridgeRel, int onlyIfFail, LoopState* loop) {
+    if (loop_done(loop)) return;
+    if (onlyIfFail && !*reinterpret_cast<volatile int*>(&loop->cholFail)) return;
+    const int n = na - 1;
+    const int64_t total = (int64_t)n * n;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(e / n), a = (int)(e % n);          // column b, row a
+        const int i = active[a + 1], j = active[b + 1];
+        double v = -G[(size_t)i * K + j];
+        if (a == b) v += av[AV_DIAG * K + i] * (1.0 + ridgeRel);
+        A[e] = v;
+    }
+}
+
+// Cholesky factorisation A = L L^T (left-looking by columns), the two triangular solves and the Newton
+// candidate f_nr = f - gamma * H^-1 g (mbar_solvers.py:581-584), all in ONE CTA.  SMEM: the matrix lives in
+// shared memory (n <= 160); otherwise it stays in global memory (L2-resident: n^2 * 8 <= 32 MB) and is read with
+// ld.global.cg so that no stale L1 line is ever seen.
+template <bool SMEM>
+__global__ void __launch_bounds__(1024)
+newton_kernel(double* __restrict__ Ag, int na, int K, const int* __restrict__ active, const double* __restrict__ f,
+              const double* __restrict__ Nk, double* __restrict__ av, double mid, int onlyIfFail, int lastAttempt,
+              LoopState* loop) {
+    if (loop_done(loop)) return;
+    if (onlyIfFail && !*reinterpret_cast<volatile int*>(&loop->cholFail)) return;
+    extern __shared__ __align__(16) double sm[];
+    const int n = na - 1;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* b = sm;                       // [n] right-hand side / solution
+    double* row = sm + ((n + 1) & ~1);    // [n] pivot row of L
+    double* M = SMEM ? row + ((n + 1) & ~1) : Ag;
+    __shared__ int s_fail;
+    if (tid == 0) s_fail = 0;
+    if (SMEM)
+        for (int e = tid; e < n * n; e += nt) M[e] = Ag[e];
+    for (int a = tid; a < n; a += nt) b[a] = av[AV_G * K + active[a + 1]];
+    __syncthreads();
+#define LDM(ptr) (SMEM ? *(ptr) : __ldcg(ptr))
+    for (int j = 0; j < n; ++j) {
+        for (int k = tid; k < j; k += nt) row[k] = LDM(M + (size_t)k * n + j);
+        __syncthreads();
+        for (int i = j + tid; i < n; i += nt) {
+            double s0 = LDM(M + (size_t)j * n + i), s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int k = 0;
+            for (; k + 4 <= j; k += 4) {
+                s0 = fma(-LDM(M + (size_t)k * n + i), row[k], s0);
+                s1 = fma(-LDM(M + (size_t)(k + 1) * n + i), row[k + 1], s1);
+                s2 = fma(-LDM(M + (size_t)(k + 2) * n + i), row[k + 2], s2);
+                s3 = fma(-LDM(M + (size_t)(k + 3) * n + i), row[k + 3], s3);
+            }
+            for (; k < j; ++k) s0 = fma(-LDM(M + (size_t)k * n + i), row[k], s0);
+            M[(size_t)j * n + i] = (s0 + s1) + (s2 + s3);
+        }
+        __syncthreads();
+        const double d = LDM(M + (size_t)j * n + j);
+        if (!(d > 0.0) || !(d < 1e300)) {       // not positive definite (or NaN): uniform exit
+            if (tid == 0) s_fail = 1;
+            break;
+        }
+        const double sq = sqrt(d), inv = 1.0 / sq;
+        __syncthreads();                          // everyone has read d before the diagonal is overwritten
+        for (int i = j + tid; i < n; i += nt) {
+            const double v = LDM(M + (size_t)j * n + i);
+            M[(size_t)j * n + i] = (i == j) ? sq : v * inv;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (s_fail) {
+        if (tid == 0) {
+            loop->cholFail = 1;
+            if (lastAttempt) loop->haveNr = 0;
+        }
+        if (lastAttempt)   // no Newton candidate this iteration: it coincides with the self-consistent one
+            for (int k = tid; k < K; k += nt) {
+                av[AV_FNR * K + k] = av[AV_FSCI * K + k];
+                av[AV_CNR * K + k] = av[AV_CSCI * K + k];
+            }
+        return;
+    }
+    // L y = g
+    for (int j = 0; j < n; ++j) {
+        if (tid == 0) b[j] = b[j] / LDM(M + (size_t)j * n + j);
+        __syncthreads();
+        const double xj = b[j];
+        for (int i = j + 1 + tid; i < n; i += nt) b[i] = fma(-LDM(M + (size_t)j * n + i), xj, b[i]);
+        __syncthreads();
+    }
+    // L^T x = y
+    for (int j = n - 1; j >= 0; --j) {
+        if (tid == 0) b[j] = b[j] / LDM(M + (size_t)j * n + j);
+        __syncthreads();
+        const double xj = b[j];
+        for (int i = tid; i < j; i += nt) b[i] = fma(-LDM(M + (size_t)i * n + j), xj, b[i]);
+        __syncthreads();
+    }
+#undef LDM
+    // candidate: f_nr = f - gamma x on the free states; gauge and unsampled states untouched
+    const double gamma = loop->gamma;
+    __shared__ int s_badnr;
+    if (tid == 0) s_badnr = 0;
+    __syncthreads();
+    for (int k = tid; k < K; k += nt) av[AV_FNR * K + k] = f[k];
+    __syncthreads();
+    for (int a = tid; a < n; a += nt) {
+        const int k = active[a + 1];
+        const double v = f[k] - gamma * b[a];
+        av[AV_FNR * K + k] = v;
+        if (!(fabs(v) < 0.5 * C_RANGE)) s_badnr = 1;     // NaN / inf / out of the supported range
+    }
+    __syncthreads();
+    if (s_badnr) {
+        for (int k = tid; k < K; k += nt) {
+            av[AV_FNR * K + k] = av[AV_FSCI * K + k];
+            av[AV_CNR * K + k] = av[AV_CSCI * K + k];
+        }
+        if (tid == 0) {
+            loop->haveNr = 0;
+            loop->cholFail = 0;
+        }
+        return;
+    }
+    for (int k = tid; k < K; k += nt) av[AV_CNR * K + k] = (Nk[k] > 0.0) ? av[AV_FNR * K + k] + log(Nk[k]) - mid : 0.0;
+    if (tid == 0) {
+        loop->haveNr = 1;
+        loop->cholFail = 0;
+    }
+}
+
+// After the two candidate passes: gradient norms, the step choice of mbar_solvers.py:607, the convergence rule
+// of :627-640, and the vectors of the next iteration.
+__global__ void __launch_bounds__(256)
+adapt_post_kernel(const double* __restrict__ outS, const double* __restrict__ outN, const double* __restrict__ av,
+                  double* __restrict__ f, double* __restrict__ c0, const double* __restrict__ Nk,
+                  const unsigned long long* __restrict__ rowmask, int K, int first, double mid, LoopState* loop) {
+    if (loop_done(loop)) return;
+    __shared__ double s_buf[64];
+    double gs = 0.0, gn = 0.0, badS = 0.0, badN = 0.0;
+    if (threadIdx.x == 0) {
+        if (outS[K + 1] != 0.0) badS = 1.0;
+        if (outN[K + 1] != 0.0) badN = 1.0;
+    }
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+        if (row_on(rowmask, k)) {
+            const double a = Nk[k] * (outS[k] - 1.0), b = Nk[k] * (outN[k] - 1.0);
+            if (!(outS[k] > 1e-280) || !(outS[k] < 1e300)) badS = 1.0;
+            if (!(outN[k] > 1e-280) || !(outN[k] < 1e300)) badN = 1.0;
+            gs += a * a;
+            gn += b * b;
+        }
+    gs = block_sum(gs, s_buf);
+    gn = block_sum(gn, s_buf);
+    badS = block_sum(badS, s_buf);
+    badN = block_sum(badN, s_buf);
+    const int haveNr = loop->haveNr && !(badN > 0.0) && gn == gn;
+    const double gnNr = haveNr ? gn : INFINITY;
+    const bool takeSci = (gs < gnNr) || (loop->sci_iterations < loop->min_sc_iter);    // mbar_solvers.py:607
+    const double* fnew = av + (takeSci ? AV_FSCI : AV_FNR) * K;
+    const double* fsci = av + AV_FSCI * K;
+    const double* fnr = haveNr ? av + AV_FNR * K : fsci;
+    const double thr = fmin(1.0e-8, loop->tol);
+    double md = 0.0, mx = 0.0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+        if (row_on(rowmask, k) && k != first) {
+            const double v = fnew[k];
+            double div = fabs(v);
+            if (div < thr) div = 1.0;
+            const double d1 = fabs(v - f[k]) / div, d2 = fabs(fsci[k] - fnr[k]) / div;
+            if (d1 != d1 || md != md) md = NAN; else md = fmax(md, d1);
+            if (d2 == d2) mx = fmax(mx, d2);
+        }
+    md = block_max_nan(md, s_buf);
+    mx = block_max_nan(mx, s_buf);
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const double v = fnew[k];
+        f[k] = v;
+        c0[k] = row_on(rowmask, k) ? v + log(Nk[k]) - mid : 0.0;
+    }
+    if (threadIdx.x == 0) {
+        const int it = loop->iterations + 1;
+        loop->iterations = it;
+        if (takeSci) loop->sci_iterations++; else loop->nr_iterations++;
+        loop->gn_sci = gs;
+        loop->gn_nr = gnNr;
+        loop->gnorm = sqrt(takeSci ? gs : gn);
+        loop->max_delta = md;
+        loop->max_diff = mx;
+        if (badS > 0.0 || md != md) {
+            // the fused kernel's range assumption failed on the self-consistent candidate, or a non-finite
+            // candidate: the host redoes this iteration on the robust stepped path
+            loop->status = (outS[K + 1] >= 1.0e6 || outN[K + 1] >= 1.0e6) ? 2 : 1;
+            loop->done = 1;
+        } else if (md < loop->tol && mx < sqrt(loop->tol)) {
+            loop->success = 1;
+            loop->done = 1;
+        } else if (it >= loop->maxiter) {
+            loop->done = 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int comm_rendezvous(mbar_b200_ctx* c) {
+    if (!c->comm || c->nranks == 1) return MBAR_B200_OK;
+    // every rank's stream reaches the first in-kernel exchange within microseconds of the others
+    return comm_allreduce(c, c->d_scratch + (size_t)c->K * c->K + 4 * (size_t)c->K, 1, 0);
+}
+
+static int loop_begin(mbar_b200_ctx* c, double tol, int maxiter, int min_sc_iter, double gamma) {
+    LoopState st{};
+    st.tol = tol;
+    st.gamma = gamma;
+    st.maxiter = maxiter;
+    st.min_sc_iter = min_sc_iter;
+    *c->h_loop = st;
+    MBAR_CUDA(cudaMemcpyAsync(c->d_loop, c->h_loop, sizeof(LoopState), cudaMemcpyHostToDevice, c->stream));
+    return MBAR_B200_OK;
+}
+
+// download LoopState + f (pinned row 5) and wait: the ONE synchronisation per batch
+static int loop_poll(mbar_b200_ctx* c) {
+    const int K = c->K;
+    MBAR_CUDA(cudaMemcpyAsync(c->h_loop, c->d_loop, sizeof(LoopState), cudaMemcpyDeviceToHost, c->stream));
+    MBAR_CUDA(cudaMemcpyAsync(c->h_f + 5 * K, c->d_f, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    MBAR_CUDA(cudaStreamSynchronize(c->stream));
+    c->d2hBytes += (int64_t)K * 8 + (int64_t)sizeof(LoopState);
+    c->loopPolls++;
+    MBAR_CUDA(cudaGetLastError());
+    return MBAR_B200_OK;
+}
+
+static bool device_loop_possible(const mbar_b200_ctx* c) {
+    if (c->kernelChoice == MBAR_B200_KERNEL_GENERIC) return false;
+    if (c->nranks > 1 && !c->comm) return false;
+    return c->K <= 2048;
+}
+
+int solve_sci_device(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter, mbar_b200_solve_result* res) {
+    MBAR_REQUIRE(c->ready, MBAR_B200_ERR_NOT_READY, "u_kn has not been uploaded");
+    MBAR_CUDA(cudaSetDevice(c->device));
+    MBAR_TRY(check_range(c, f));
+    const int K = c->K;
+    const int g0 = c->firstActive;
+    if (!device_loop_possible(c) || maxiter < 1 || c->active.size() < 2)
+        return solve_sci_stepped(c, f, tol, maxiter, res);
+    std::vector<double> cur(f, f + K), snap(K);
+    for (int k : c->active) cur[k] -= f[g0];
+    mbar_b200_solve_result r{};
+    cudaEvent_t e0, e1;
+    MBAR_CUDA(cudaEventCreate(&e0));
+    MBAR_CUDA(cudaEventCreate(&e1));
+    MBAR_CUDA(cudaEventRecord(e0, c->stream));
+    MBAR_TRY(loop_begin(c, tol, maxiter, 0, 1.0));
+    const bool inKernel = (c->nranks == 1 || c->peerReady) && !std::getenv("MBAR_B200_NO_FUSED_EPILOGUE");
+    if (c->peerReady && inKernel) MBAR_TRY(comm_rendezvous(c));
+    const int threads = 256;
+    bool fallback = false;
+    int itersBefore = 0;
+    int rc = MBAR_B200_OK;
+    for (;;) {
+        snap = cur;
+        itersBefore = c->h_loop->iterations;
+        FusedParams p;
+        bool ok = false;
+        MBAR_TRY(fused_prepare(c, cur.data(), false, false, &p, &ok));
+        if (!ok) { fallback = true; break; }
+        std::memcpy(c->h_f + 4 * K, cur.data(), K * sizeof(double));
+        MBAR_CUDA(cudaMemcpyAsync(c->d_f, c->h_f + 4 * K, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        c->h2dBytes += K * 8;
+        p.loop = c->d_loop;
+        p.first = g0;
+        if (inKernel) {
+            p.epi = 1;
+            p.f = c->d_f;
+            p.cnext = c->d_c;
+            if (c->peerReady) p.peer = c->peer;
+        }
+        for (int b = 0; b < c->loopBatch; ++b) {
+            MBAR_TRY(fused_enqueue(c, p));
+            if (!inKernel) {
+                MBAR_TRY(comm_allreduce(c, c->d_out, K + 2, 0));
+                sci_loop_epilogue_kernel<<<1, threads, 0, c->stream>>>(c->d_out, c->d_f, c->d_c, c->d_Nk, c->d_rowmask,
+                                                                      K, g0, p.mid, c->d_loop);
+                c->launches++;
+            }
+        }
+        MBAR_TRY(loop_poll(c));
+        const LoopState& st = *c->h_loop;
+        if (st.status != 0) {
+            MBAR_REQUIRE(st.status != 2, MBAR_B200_ERR_COMM,
+                         "peer exchange timed out inside the pass kernel (a rank did not arrive)");
+            fallback = true;
+            break;
+        }
+        std::memcpy(cur.data(), c->h_f + 5 * K, K * sizeof(double));
+        if (st.done) break;
+    }
+    const LoopState st = *c->h_loop;
+    r.iterations = r.sci_iterations = st.iterations;
+    r.passes = st.iterations;
+    r.success = st.success;
+    r.max_delta = st.max_delta;
+    if (fallback) {
+        // redo from the last good f on the robust path (generic kernel, log-domain sums)
+        mbar_b200_solve_result r2{};
+        const int done = itersBefore;
+        rc = solve_sci_stepped(c, snap.data(), tol, maxiter - done > 1 ? maxiter - done : 1, &r2);
+        cur = snap;
+        r2.iterations += done;
+        r2.sci_iterations += done;
+        r2.passes += done;
+        r = r2;
+    } else {
+        // gradient norm at the returned f (mbar_solvers.py:938-940): one more pass
+        rc = run_pass(c, cur.data(), PassWant{});
+        r.passes++;
+        double gn = 0.0;
+        for (int k : c->active) {
+            const double g = c->h_Nk[k] * (c->h_out[k] - 1.0);
+            gn += g * g;
+        }
+        r.gnorm = std::sqrt(gn);
+    }
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    r.device_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc == MBAR_B200_OK)
+        for (int k : c->active) f[k] = cur[k];
+    if (res) *res = r;
+    return rc;
+}
+
+// One adaptive iteration, enqueued with no host synchronisation.
+static int enqueue_adaptive_iteration(mbar_b200_ctx* c, const FusedParams& pF, const FusedParams& pS,
+                                      const FusedParams& pN) {
+    const int K = c->K;
+    const PassLayout lay{K};
+    const int na = (int)c->active.size();
+    const int n = na - 1;
+    const int g0 = c->firstActive;
+    const bool nccl = c->nranks > 1 && !c->peerReady;
+    double* av = c->d_av;
+    // (1) pass at f: S, sum L, per-sample L'_n
+    MBAR_TRY(fused_enqueue(c, pF));
+    if (nccl) MBAR_TRY(comm_allreduce(c, c->d_out, K + 2, 0));
+    adapt_pre_kernel<<<1, 256, 0, c->stream>>>(c->d_out, c->d_f, c->d_Nk, c->d_rowmask, K, g0, pF.mid, av, c->d_loop);
+    // (2) second moments at f (reads L'_n of the pass above)
+    MBAR_TRY(launch_hessian_dev(c, av + AV_CH * K, false, c->d_loop));
+    if (c->nranks > 1) MBAR_TRY(comm_allreduce(c, c->d_out + lay.G(), K * K, 0));
+    // (3) Newton candidate: build, factorise, solve; one retry with a relative ridge if not positive definite
+    const bool smem = (size_t)n * n * 8 + 2 * ((size_t)n + 2) * 8 <= 200 * 1024;
+    const size_t shBytes = 2 * ((size_t)n + 2) * 8 + (smem ? (size_t)n * n * 8 : 0);
+    auto kern = smem ? newton_kernel<true> : newton_kernel<false>;
+    static size_t attr[16][2] = {{0}};
+    size_t& a = attr[c->device & 15][smem ? 0 : 1];
+    if (a < shBytes) {
+        MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shBytes));
+        a = shBytes;
+    }
+    const int bgrid = (int)std::min<int64_t>(((int64_t)n * n + 255) / 256, 4 * c->smCount);
+    const int nthreads = n >= 512 ? 1024 : n >= 128 ? 512 : 256;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        newton_build_kernel<<<bgrid, 256, 0, c->stream>>>(c->d_out + lay.G(), av, c->d_active, na, K, c->d_A,
+                                                         attempt ? 1.0e-10 : 0.0, attempt, c->d_loop);
+        kern<<<1, nthreads, shBytes, c->stream>>>(c->d_A, na, K, c->d_active, c->d_f, c->d_Nk, av, pF.mid, attempt,
+                                                 attempt == 1, c->d_loop);
+    }
+    MBAR_CUDA(cudaGetLastError());
+    // (4) both candidates
+    MBAR_TRY(fused_enqueue(c, pS));
+    if (nccl) MBAR_TRY(comm_allreduce(c, pS.out, K + 2, 0));
+    MBAR_TRY(fused_enqueue(c, pN));
+    if (nccl) MBAR_TRY(comm_allreduce(c, pN.out, K + 2, 0));
+    // (5) choice + convergence + next iteration's vectors
+    adapt_post_kernel<<<1, 256, 0, c->stream>>>(pS.out, pN.out, av, c->d_f, c->d_c, c->d_Nk, c->d_rowmask, K, g0,
+                                               pF.mid, c->d_loop);
+    MBAR_CUDA(cudaGetLastError());
+    c->launches += 6;
+    return MBAR_B200_OK;
+}
+
+int solve_adaptive_device(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter, int32_t min_sc_iter,
+                          double gamma, mbar_b200_solve_result* res) {
+    MBAR_REQUIRE(c->ready, MBAR_B200_ERR_NOT_READY, "u_kn has not been uploaded");
+    MBAR_CUDA(cudaSetDevice(c->device));
+    MBAR_TRY(check_range(c, f));
+    const int K = c->K;
+    const int g0 = c->firstActive;
+    const int na = (int)c->active.size();
+    if (!device_loop_possible(c) || maxiter < 1 || na < 2)
+        return solve_adaptive_stepped(c, f, tol, maxiter, min_sc_iter, gamma, res);
+    std::vector<double> cur(f, f + K), snap(K);
+    for (int k : c->active) cur[k] -= f[g0];
+    mbar_b200_solve_result r{};
+    cudaEvent_t e0, e1;
+    MBAR_CUDA(cudaEventCreate(&e0));
+    MBAR_CUDA(cudaEventCreate(&e1));
+    MBAR_CUDA(cudaEventRecord(e0, c->stream));
+    MBAR_TRY(loop_begin(c, tol, maxiter, min_sc_iter, gamma));
+    if (c->peerReady) MBAR_TRY(comm_rendezvous(c));
+    bool fallback = false;
+    int itersBefore = 0;
+    int rc = MBAR_B200_OK;
+    for (;;) {
+        snap = cur;
+        itersBefore = c->h_loop->iterations;
+        FusedParams pF;
+        bool ok = false;
+        MBAR_TRY(fused_prepare(c, cur.data(), true, false, &pF, &ok));
+        if (!ok) { fallback = true; break; }
+        std::memcpy(c->h_f + 4 * K, cur.data(), K * sizeof(double));
+        MBAR_CUDA(cudaMemcpyAsync(c->d_f, c->h_f + 4 * K, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        c->h2dBytes += K * 8;
+        pF.loop = c->d_loop;
+        pF.first = g0;
+        if (c->peerReady) pF.peer = c->peer;
+        FusedParams pS = pF, pN = pF;
+        pS.c = c->d_av + AV_CSCI * K;
+        pS.out = c->d_outM;
+        pS.Lout = nullptr;
+        pN.c = c->d_av + AV_CNR * K;
+        pN.out = c->d_outM + PassLayout{K}.size(false);
+        pN.Lout = nullptr;
+        for (int b = 0; b < c->loopBatch; ++b) MBAR_TRY(enqueue_adaptive_iteration(c, pF, pS, pN));
+        MBAR_TRY(loop_poll(c));
+        const LoopState& st = *c->h_loop;
+        if (st.status != 0) {
+            MBAR_REQUIRE(st.status != 2, MBAR_B200_ERR_COMM,
+                         "peer exchange timed out inside the pass kernel (a rank did not arrive)");
+            fallback = true;
+            break;
+        }
+        std::memcpy(cur.data(), c->h_f + 5 * K, K * sizeof(double));
+        if (st.done) break;
+    }
+    const LoopState st = *c->h_loop;
+    r.iterations = st.iterations;
+    r.nr_iterations = st.nr_iterations;
+    r.sci_iterations = st.sci_iterations;
+    r.passes = 3 * st.iterations;
+    r.hessian_passes = st.iterations;
+    r.success = st.success;
+    r.max_delta = st.max_delta;
+    r.gnorm = st.gnorm;
+    if (fallback) {
+        mbar_b200_solve_result r2{};
+        const int left = maxiter - itersBefore > 1 ? maxiter - itersBefore : 1;
+        const int msi = min_sc_iter - st.sci_iterations > 0 ? min_sc_iter - st.sci_iterations : 0;
+        rc = solve_adaptive_stepped(c, snap.data(), tol, left, msi, gamma, &r2);
+        cur = snap;
+        r2.iterations += itersBefore;
+        r2.passes += 3 * itersBefore;
+        r2.hessian_passes += itersBefore;
+        r = r2;
+    }
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    r.device_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc == MBAR_B200_OK)
+        for (int k : c->active) f[k] = cur[k];
+    if (res) *res = r;
+    return rc;
+}
+
+}  // namespace mbar

@@ -193,6 +193,10 @@ __device__ __forceinline__ void cluster_barrier() {
 template <int R, bool FULL, int CW, int BATCH, int MODE, int CL>
 __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    // device-resident loops: a converged (or failed) solver turns the rest of the enqueued batch into no-ops.
+    // `done` is only written by the last CTA of a launch, after every CTA has taken its ticket, so all CTAs
+    // (and all ranks: the state is bit-identical everywhere) take the same branch.
+    if (p.loop && *reinterpret_cast<volatile int*>(&p.loop->done)) return;
     const int K = p.K;
     const int half = (CL > 1) ? (int)cluster_ctarank() : 0;             // rank of this CTA in its cluster
     const int kbase = (CL > 1) ? half * p.Kh : 0;                        // first state of this CTA
@@ -425,7 +429,11 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
         // One-shot all-gather of the K+2 partial sums through peer memory (NVLink stores into every
         // rank's inbox, then a release flag), followed by a sum in RANK ORDER so that every GPU
         // computes bit-identical totals.  Replaces ncclAllReduce + a separate epilogue launch.
-        const int par = (int)(p.seq & 1ull);
+        __shared__ unsigned long long s_seq;
+        if (threadIdx.x == 0) s_seq = ++(*p.peer.seq);   // only this CTA of this launch touches the counter
+        __syncthreads();
+        const unsigned long long seq = s_seq;
+        const int par = (int)(seq & 1ull);
         const int P = p.peer.nranks, me = p.peer.rank;
         for (int q = 0; q < P; ++q) {
             double* dst = p.peer.inbox[q] + ((size_t)par * P + me) * (K + 2);
@@ -435,7 +443,7 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
         __syncthreads();
         if (threadIdx.x < P) {
             unsigned long long* flag = p.peer.flags[threadIdx.x] + (size_t)par * P + me;
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(p.seq) : "memory");
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
         }
         __shared__ int s_timeout;
         if (threadIdx.x == 0) s_timeout = 0;
@@ -446,8 +454,11 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
             unsigned long long v;
             for (;;) {
                 asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-                if (v == p.seq) break;
-                if (clock64() - t0 > 4000000000ll) {   // ~2 s: a peer died; fail instead of hanging the GPU
+                if (v == seq) break;
+                // ~20 s: a peer died; fail instead of hanging the GPU.  (The host lines the ranks up with a
+                // stream-ordered all-reduce before the first exchange of every loop, so live ranks arrive
+                // within microseconds of each other.)
+                if (clock64() - t0 > 40000000000ll) {
                     s_timeout = 1;
                     break;
                 }
@@ -481,14 +492,59 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
     if (p.epi) {
         __syncthreads();
         __shared__ double s_f0;
+        __shared__ double s_md[32];
+        __shared__ int s_nan[32];
         if (threadIdx.x == 0) s_f0 = p.f[p.first] - log(tot[p.first]);
         __syncthreads();
+        // relative change of this step (mbar_solvers.py:627-631): entries with |f| below min(1e-8, tol) are
+        // compared absolutely, the gauge state is skipped
+        const double thr = p.loop ? fmin(1.0e-8, p.loop->tol) : 1.0e-8;
+        double md = 0.0;
+        int sawNan = 0;
         for (int k = threadIdx.x; k < K; k += blockDim.x) {
-            if (p.Nk[k] > 0.0) {
+            if (p.Nk[k] > 0.0 && ((p.rowmask[k >> 6] >> (k & 63)) & 1ull)) {
                 // an underflowed S_k poisons the result so the host redoes the step in the log domain
-                const double fn = (tot[k] > 1e-280) ? p.f[k] - log(tot[k]) - s_f0 : NAN;
+                const double fo = p.f[k];
+                const double fn = (tot[k] > 1e-280) ? fo - log(tot[k]) - s_f0 : NAN;
                 p.f[k] = fn;
                 p.cnext[k] = fn + log(p.Nk[k]) - p.mid;
+                if (fn != fn) sawNan = 1;
+                if (k != p.first) {
+                    double div = fabs(fn);
+                    if (div < thr) div = 1.0;
+                    md = fmax(md, fabs(fn - fo) / div);
+                }
+            }
+        }
+        if (p.loop) {
+            for (int o = 16; o > 0; o >>= 1) md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+            sawNan = __any_sync(0xffffffffu, sawNan);
+            if (lane == 0) {
+                s_md[warp] = md;
+                s_nan[warp] = sawNan;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double m = 0.0;
+                int nn = 0;
+                for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) {
+                    m = fmax(m, s_md[w2]);
+                    nn |= s_nan[w2];
+                }
+                LoopState* L = p.loop;
+                const int it = L->iterations + 1;
+                L->iterations = it;
+                L->sci_iterations = it;
+                L->max_delta = m;
+                if (nn || tot[K + 1] != 0.0) {
+                    L->status = tot[K + 1] >= 1.0e6 ? 2 : 1;   // comm time-out | range problem: robust redo
+                    L->done = 1;
+                } else if (m < L->tol) {
+                    L->success = 1;
+                    L->done = 1;
+                } else if (it >= L->maxiter) {
+                    L->done = 1;
+                }
             }
         }
     }
@@ -515,7 +571,9 @@ bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, bool allState
 
 // Configure the fused kernel for f (host) and stage c = f + log N - mid on the device.
 int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, FusedParams* out,
-                  bool* ok) {
+                  bool* ok, double* d_cdst, double* h_stage) {
+    if (!d_cdst) d_cdst = ctx->d_c;
+    if (!h_stage) h_stage = ctx->h_f;
     *ok = false;
     double mid = 0.0, spread = 0.0;
     if (!fused_applicable(ctx, h_f, allStates, &mid, &spread)) return MBAR_B200_OK;
@@ -567,7 +625,7 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allSta
     p.nTiles = ctx->nTiles;
     p.mid = mid;
     p.u = ctx->d_u;
-    p.c = ctx->d_c;
+    p.c = d_cdst;
     // allStates: unsampled rows take part with weight e^-80 (see LOG_EPS_UNSAMPLED)
     p.rowmask = allStates ? ctx->d_onesmask : ctx->d_rowmask;
     p.Nk = allStates ? ctx->d_NkEff : ctx->d_Nk;
@@ -580,8 +638,8 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allSta
     p.wgt = ctx->d_wgt;
     p.sumW = ctx->d_wgt ? ctx->sumW : (double)ctx->N;
     for (int k = 0; k < K; ++k)
-        ctx->h_f[k] = (!allStates && std::isinf(ctx->h_logNk[k])) ? 0.0 : h_f[k] + ctx->h_logNkEff[k] - mid;
-    MBAR_CUDA(cudaMemcpyAsync(ctx->d_c, ctx->h_f, (size_t)K * sizeof(double), cudaMemcpyHostToDevice,
+        h_stage[k] = (!allStates && std::isinf(ctx->h_logNk[k])) ? 0.0 : h_f[k] + ctx->h_logNkEff[k] - mid;
+    MBAR_CUDA(cudaMemcpyAsync(d_cdst, h_stage, (size_t)K * sizeof(double), cudaMemcpyHostToDevice,
                               ctx->stream));
     ctx->h2dBytes += K * 8;
     *out = p;
@@ -609,6 +667,11 @@ int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
     PICK(8, 1, 0) PICK(16, 1, 4) PICK(32, 1, 8) PICK(32, 2, 12) PICK(32, 4, 16) PICK(32, 8, 20)
 #undef PICK
     MBAR_REQUIRE(kern, MBAR_B200_ERR_INVALID, "no fused kernel variant for K=%d", p.K);
+    snprintf(ctx->lastKernel, sizeof(ctx->lastKernel),
+             "pass_fused_kernel<R=%d, %s, CW=8, BATCH=8, MODE=%d (%s), CL=%d> grid=%lld NS=%d TPW=%d", Rt,
+             full ? "FULL" : "MASKED", (p.mode & 2) ? 3 : 1,
+             (p.mode & 2) ? "LDS table + multiplicative state constant" : "LDS table", p.CL, (long long)grid, p.NS,
+             p.TPW);
     static size_t attrSetAll[16][24] = {{0}};          // per device: the attribute belongs to the context
     size_t* attrSet = attrSetAll[ctx->device & 15];
     if (attrSet[which] < smem) {

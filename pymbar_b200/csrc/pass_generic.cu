@@ -211,6 +211,8 @@ int launch_pass_generic(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool 
     if (grid > MAX_GRID) grid = MAX_GRID;
     auto kern = needUnsampled ? pass_generic_kernel<true> : pass_generic_kernel<false>;
     MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    snprintf(ctx->lastKernel, sizeof(ctx->lastKernel), "pass_generic_kernel<%s> grid=%lld warps=%d",
+             needUnsampled ? "log-domain rows" : "linear rows", (long long)grid, W);
     MBAR_CUDA(cudaEventRecord(ctx->evA, ctx->stream));
     kern<<<(unsigned)grid, W * 32, smem, ctx->stream>>>(ctx->d_u, K, ctx->N, ctx->nTiles, ctx->d_c,
                                                        ctx->d_c + K, ctx->d_rowmask,

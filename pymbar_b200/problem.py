@@ -191,6 +191,16 @@ class DeviceProblem:
                                        _dptr(G) if want_G else None))
         return S, sumL.value, G
 
+    def pass_multi(self, f_mk):
+        """One call, one synchronisation, M (1 or 2) candidate vectors: returns (S[M, K], sumL[M])."""
+        f = np.ascontiguousarray(f_mk, dtype=np.float64)
+        if f.ndim != 2 or f.shape[1] != self.K or not 1 <= f.shape[0] <= 2:
+            raise ValueError(f"expected [M in (1, 2), {self.K}], got {f.shape}")
+        S = np.empty_like(f)
+        sumL = np.empty(f.shape[0])
+        check(self._lib.mbar_b200_pass_multi(self._h, f.shape[0], _dptr(f), _dptr(S), _dptr(sumL)))
+        return S, sumL
+
     def self_consistent_update(self, f_k):
         f = _f64(f_k, self.K)
         if self._bad(f):
@@ -272,7 +282,35 @@ class DeviceProblem:
                                                  float(gamma), C.byref(r)))
         return f, self._result(r)
 
+    def set_loop_mode(self, mode="device", batch=0):
+        """'device' (default): solver iterations stay on the GPU, polled every `batch` iterations;
+        'stepped': one host round trip per pass (round-1 behaviour, also the robust fallback)."""
+        code = {"device": 0, "stepped": 1}.get(mode, mode)
+        check(self._lib.mbar_b200_set_loop_mode(self._h, int(code), int(batch)))
+
+    def loop_stats(self):
+        polls, mode, batch = C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        check(self._lib.mbar_b200_get_loop_stats(self._h, C.byref(polls), C.byref(mode), C.byref(batch)))
+        return dict(polls=polls.value, mode="stepped" if mode.value else "device", batch=batch.value)
+
+    def last_kernels(self):
+        a, b = C.create_string_buffer(256), C.create_string_buffer(256)
+        check(self._lib.mbar_b200_last_kernels(self._h, a, b, 256))
+        return dict(pass_kernel=a.value.decode(), hessian_kernel=b.value.decode())
+
+    def last_hessian_ms(self):
+        w, h = C.c_double(0), C.c_double(0)
+        check(self._lib.mbar_b200_last_hessian_ms(self._h, C.byref(w), C.byref(h)))
+        return dict(weights_ms=w.value, hessian_ms=h.value)
+
     def sci_iterate(self, f_k, iters):
         f = _f64(f_k, self.K).copy()
         check(self._lib.mbar_b200_sci_iterate(self._h, _dptr(f), int(iters)))
         return f
+
+
+def measure_fp64_peak(device=0):
+    """(DMMA TFLOP/s, DFMA TFLOP/s) of this GPU from register-only loops (mbar_b200_measure_fp64_peak)."""
+    a, b = C.c_double(0), C.c_double(0)
+    check(_lib.load().mbar_b200_measure_fp64_peak(int(device), C.byref(a), C.byref(b)))
+    return a.value, b.value
