@@ -147,6 +147,10 @@ int mbar_b200_hessian(mbar_b200_ctx* ctx, const double* f_k, double* H_out);
  * row stride ld_out elements; exponentiate != 0 gives mbar_W_nk (mbar_solvers.py:476-507). */
 int mbar_b200_log_W_nk(mbar_b200_ctx* ctx, const double* f_k, double* logW_host, int64_t ld_out,
                        int exponentiate);
+/* Rows [n0, n0 + n) of the same matrix (n0 a multiple of 32): lets a caller page through Log_W_nk, or fetch the
+ * part an estimator needs, instead of materialising N x K doubles on the host (mbar.py:455 keeps all of it). */
+int mbar_b200_log_W_nk_rows(mbar_b200_ctx* ctx, const double* f_k, int64_t n0, int64_t n, double* logW_host,
+                            int64_t ld_out, int exponentiate);
 /* Sums and second moments of the weights of ALL K states (sampled or not) at f_k:
  *   S[K] = sum_n W_nk,  G[K*K] = W^T W.
  * Everything MBAR's asymptotic covariance (mbar.py:1837-1858, "svd-ew"), compute_overlap (mbar.py:605-606) and

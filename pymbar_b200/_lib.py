@@ -64,6 +64,7 @@ SIGNATURES = {
     "mbar_b200_hessian": (C.c_int, [_ctx, _dp, _dp]),
     "mbar_b200_weight_moments": (C.c_int, [_ctx, _dp, _dp, _dp]),
     "mbar_b200_log_W_nk": (C.c_int, [_ctx, _dp, C.c_void_p, C.c_int64, C.c_int]),
+    "mbar_b200_log_W_nk_rows": (C.c_int, [_ctx, _dp, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int]),
     "mbar_b200_log_denominator": (C.c_int, [_ctx, _dp, _dp]),
     "mbar_b200_solve_sci": (C.c_int, [_ctx, _dp, C.c_double, C.c_int32, C.POINTER(SolveResult)]),
     "mbar_b200_solve_adaptive": (C.c_int, [_ctx, _dp, C.c_double, C.c_int32, C.c_int32, C.c_double,

@@ -442,7 +442,19 @@ int mbar_b200_log_W_nk(mbar_b200_ctx* c, const double* f, double* logW, int64_t 
     PassWant w;
     w.L = true;
     MBAR_TRY(run_pass(c, f, w));
-    return launch_logw(c, f, logW, ld, expo);
+    return launch_logw(c, f, logW, ld, expo, 0, c->N);
+}
+
+int mbar_b200_log_W_nk_rows(mbar_b200_ctx* c, const double* f, int64_t n0, int64_t n, double* logW, int64_t ld,
+                            int expo) {
+    MBAR_REQUIRE(logW, MBAR_B200_ERR_INVALID, "logW_host is NULL");
+    MBAR_REQUIRE(c && ld >= c->K, MBAR_B200_ERR_INVALID, "ld_out < K");
+    MBAR_REQUIRE(n0 >= 0 && n >= 1 && n0 + n <= c->N && n0 % TILE_N == 0, MBAR_B200_ERR_INVALID,
+                 "rows [%lld, +%lld): n0 must be a multiple of 32 inside [0, N_local)", (long long)n0, (long long)n);
+    PassWant w;
+    w.L = true;
+    MBAR_TRY(run_pass(c, f, w));
+    return launch_logw(c, f, logW, ld, expo, n0, n);
 }
 
 int mbar_b200_log_denominator(mbar_b200_ctx* c, const double* f, double* L_host) {

@@ -235,7 +235,8 @@ bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, bool allState
 int launch_hessian(mbar_b200_ctx* ctx, const double* h_f, bool allRows);
 // same with c_k = f_k + log N_k already on the device (device-resident loops); loop may be NULL
 int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, LoopState* loop);
-int launch_logw(mbar_b200_ctx* ctx, const double* h_f, double* logW_host, int64_t ld, int expo);
+int launch_logw(mbar_b200_ctx* ctx, const double* h_f, double* logW_host, int64_t ld, int expo, int64_t n0,
+                int64_t n);
 int launch_synth(mbar_b200_ctx* ctx, const mbar_b200_synth* spec);
 int launch_untile(mbar_b200_ctx* ctx, int64_t n0, int64_t n, double* d_dst, int64_t ld);
 int comm_allreduce(mbar_b200_ctx* ctx, double* d_buf, int count, int op /*0 sum, 2 max*/);

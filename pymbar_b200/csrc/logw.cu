@@ -1,7 +1,11 @@
 // mbar_log_W_nk / mbar_W_nk (mbar_solvers.py:439-507): logW[n, k] = f_k - u_kn - L_n, [N, K] row-major.
 // Reads the tile-major u' once (+ the stored L'_n) and writes the transposed [N, K] layout through a
 // 32 x 33 shared-memory transposition buffer per warp, so both the read and the write are coalesced.
+#include <algorithm>
 #include <cmath>
+#include <cstring>
+#include <thread>
+#include <vector>
 
 #include "internal.cuh"
 
@@ -19,7 +23,9 @@ logw_kernel(const double* __restrict__ u, const double* __restrict__ Lp, const d
     for (int k0 = warp * 32; k0 < K; k0 += 4 * 32) {
         const int kmax = min(32, K - k0);
         for (int kk = 0; kk < kmax; ++kk) {
-            double v = f[k0 + kk] - tp[(int64_t)(k0 + kk) * TILE_N] - L;
+            const double uu = tp[(int64_t)(k0 + kk) * TILE_N];
+            // energies clamped at upload (+inf in the caller's array) have weight exactly 0, as in the reference
+            double v = (uu >= U_CLAMP) ? -INFINITY : f[k0 + kk] - uu - L;
             if (expo) v = exp(v);
             t[kk * 33 + lane] = v;
         }
@@ -34,40 +40,96 @@ logw_kernel(const double* __restrict__ u, const double* __restrict__ Lp, const d
     }
 }
 
-// Requires ctx->d_L from a pass at the same f.  Streams [N, K] to the host in chunks.
-int launch_logw(mbar_b200_ctx* ctx, const double* h_f, double* logW_host, int64_t ld, int expo) {
+// Requires ctx->d_L from a pass at the same f.  Streams rows [n0, n0 + n) of the [N, K] result to the host in
+// chunks (n0 must be a multiple of 32).  A pinned destination is written by DMA directly; a pageable one (what
+// numpy hands over) goes through two pinned staging buffers that several host threads drain in parallel while the
+// next chunk is computed and copied — the driver's own pageable path is a single synchronous bounce.
+int launch_logw(mbar_b200_ctx* ctx, const double* h_f, double* logW_host, int64_t ld, int expo, int64_t n0,
+                int64_t n) {
     const int K = ctx->K;
     MBAR_REQUIRE(ctx->d_L, MBAR_B200_ERR_NOT_READY, "log_W: per-sample L not available");
+    MBAR_REQUIRE(n0 >= 0 && n >= 1 && n0 + n <= ctx->N && n0 % TILE_N == 0, MBAR_B200_ERR_INVALID,
+                 "log_W rows [%lld, +%lld): n0 must be a multiple of 32 inside [0, N)", (long long)n0, (long long)n);
+    NvtxRange nvtx_("mbar_b200::log_W download");
     for (int k = 0; k < K; ++k) ctx->h_f[3 * K + k] = h_f[k];
     MBAR_CUDA(cudaMemcpyAsync(ctx->d_c + 3 * K, ctx->h_f + 3 * K, (size_t)K * sizeof(double),
                               cudaMemcpyHostToDevice, ctx->stream));
+    cudaPointerAttributes attr;
+    bool pinnedDst = false;
+    if (cudaPointerGetAttributes(&attr, logW_host) == cudaSuccess)
+        pinnedDst = (attr.type == cudaMemoryTypeHost);
+    else
+        cudaGetLastError();
+    const int64_t tileFirst = n0 / TILE_N;
+    const int64_t tilesTotal = (n + TILE_N - 1) / TILE_N;
     int64_t tilesPerChunk = (64ll << 20) / ((int64_t)K * TILE_N * 8);
     if (tilesPerChunk < 1) tilesPerChunk = 1;
-    if (tilesPerChunk > ctx->nTiles) tilesPerChunk = ctx->nTiles;
+    if (tilesPerChunk > tilesTotal) tilesPerChunk = tilesTotal;
     double* d_out[2] = {nullptr, nullptr};
+    double* h_stage[2] = {nullptr, nullptr};
     const size_t chunkBytes = (size_t)tilesPerChunk * TILE_N * K * sizeof(double);
-    for (int i = 0; i < 2; ++i) MBAR_CUDA(cudaMalloc((void**)&d_out[i], chunkBytes));
+    for (int i = 0; i < 2; ++i) {
+        MBAR_CUDA(cudaMalloc((void**)&d_out[i], chunkBytes));
+        if (!pinnedDst) MBAR_CUDA(cudaHostAlloc((void**)&h_stage[i], chunkBytes, cudaHostAllocDefault));
+    }
     int rc = MBAR_B200_OK;
     cudaEvent_t done[2];
     for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+    struct Pending { int64_t row0 = 0, rows = 0; bool live = false; } pend[2];
+    // drain staging buffer `b` into the caller's (pageable) array with several threads
+    auto drain = [&](int b) {
+        if (!pend[b].live) return;
+        cudaEventSynchronize(done[b]);
+        const int64_t rows = pend[b].rows;
+        double* dst = logW_host + (pend[b].row0 - n0) * ld;
+        const double* src = h_stage[b];
+        const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({8, rows, (int64_t)std::thread::hardware_concurrency()}));
+        auto work = [&](int t) {
+            const int64_t r0 = rows * t / nthr, r1 = rows * (t + 1) / nthr;
+            if (ld == K) {
+                std::memcpy(dst + r0 * K, src + r0 * K, (size_t)(r1 - r0) * K * sizeof(double));
+            } else {
+                for (int64_t r = r0; r < r1; ++r) std::memcpy(dst + r * ld, src + r * K, (size_t)K * sizeof(double));
+            }
+        };
+        if (nthr == 1 || (size_t)rows * K < (1u << 16)) {
+            for (int t = 0; t < nthr; ++t) work(t);
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 1; t < nthr; ++t) th.emplace_back(work, t);
+            work(0);
+            for (auto& x : th) x.join();
+        }
+        pend[b].live = false;
+    };
     int buf = 0;
-    for (int64_t t0 = 0; t0 < ctx->nTiles; t0 += tilesPerChunk, buf ^= 1) {
-        const int64_t nt = (ctx->nTiles - t0 < tilesPerChunk) ? (ctx->nTiles - t0) : tilesPerChunk;
-        const int64_t row0 = t0 * TILE_N;
-        const int64_t rows = ((row0 + nt * TILE_N > ctx->N) ? ctx->N : row0 + nt * TILE_N) - row0;
+    for (int64_t t0 = 0; t0 < tilesTotal; t0 += tilesPerChunk, buf ^= 1) {
+        const int64_t nt = (tilesTotal - t0 < tilesPerChunk) ? (tilesTotal - t0) : tilesPerChunk;
+        const int64_t row0 = n0 + t0 * TILE_N;
+        const int64_t rows = ((row0 + nt * TILE_N > n0 + n) ? n0 + n : row0 + nt * TILE_N) - row0;
+        if (!pinnedDst) drain(buf);     // the staging buffer of two chunks ago must be empty again
         // kernel on `stream` must wait until the previous D2H out of this buffer finished
         cudaStreamWaitEvent(ctx->stream, done[buf], 0);
         logw_kernel<<<(unsigned)nt, 128, 0, ctx->stream>>>(ctx->d_u, ctx->d_L, ctx->d_c + 3 * K, K, ctx->N,
-                                                          t0, d_out[buf], expo);
+                                                          tileFirst + t0, d_out[buf], expo);
         ctx->launches++;
         cudaEvent_t ready;
         cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
         cudaEventRecord(ready, ctx->stream);
         cudaStreamWaitEvent(ctx->copyStream, ready, 0);
         cudaEventDestroy(ready);
-        cudaError_t e = cudaMemcpy2DAsync(logW_host + row0 * ld, (size_t)ld * sizeof(double), d_out[buf],
-                                          (size_t)K * sizeof(double), (size_t)K * sizeof(double),
-                                          (size_t)rows, cudaMemcpyDeviceToHost, ctx->copyStream);
+        cudaError_t e;
+        if (pinnedDst) {
+            e = cudaMemcpy2DAsync(logW_host + (row0 - n0) * ld, (size_t)ld * sizeof(double), d_out[buf],
+                                  (size_t)K * sizeof(double), (size_t)K * sizeof(double), (size_t)rows,
+                                  cudaMemcpyDeviceToHost, ctx->copyStream);
+        } else {
+            e = cudaMemcpyAsync(h_stage[buf], d_out[buf], (size_t)rows * K * sizeof(double), cudaMemcpyDeviceToHost,
+                                ctx->copyStream);
+            pend[buf].row0 = row0;
+            pend[buf].rows = rows;
+            pend[buf].live = true;
+        }
         cudaEventRecord(done[buf], ctx->copyStream);
         ctx->d2hBytes += rows * K * 8;
         if (e != cudaSuccess) {
@@ -83,9 +145,14 @@ int launch_logw(mbar_b200_ctx* ctx, const double* h_f, double* logW_host, int64_
         set_error("log_W failed: %s", cudaGetErrorString(e));
         rc = MBAR_B200_ERR_CUDA;
     }
+    if (!pinnedDst && rc == MBAR_B200_OK) {
+        drain(0);
+        drain(1);
+    }
     for (int i = 0; i < 2; ++i) {
         cudaEventDestroy(done[i]);
         cudaFree(d_out[i]);
+        if (h_stage[i]) cudaFreeHost(h_stage[i]);
     }
     return rc;
 }

@@ -250,16 +250,29 @@ class DeviceProblem:
         check(self._lib.mbar_b200_weight_moments(self._h, _dptr(f), _dptr(S), _dptr(G)))
         return S, G
 
-    def log_W_nk(self, f_k, exponentiate=False, out=None):
+    def log_W_nk(self, f_k, exponentiate=False, out=None, rows=None, row0=0):
+        """[N, K] log weights (mbar_solvers.py:439-473); `rows` / `row0` (multiple of 32) fetch a block of rows."""
         f = _f64(f_k, self.K)
+        if self._bad(f):
+            n = self.N if rows is None else int(rows)
+            return np.full((n, self.K), np.nan)
+        if rows is None and row0 == 0:
+            if out is None:
+                out = np.empty((self.N, self.K), np.float64)
+            check(self._lib.mbar_b200_log_W_nk(self._h, _dptr(f), C.c_void_p(out.ctypes.data),
+                                               out.strides[0] // 8, int(bool(exponentiate))))
+            return out
+        rows = self.N - row0 if rows is None else int(rows)
         if out is None:
-            out = np.empty((self.N, self.K), np.float64)
-        check(self._lib.mbar_b200_log_W_nk(self._h, _dptr(f), C.c_void_p(out.ctypes.data),
-                                           out.strides[0] // 8, int(bool(exponentiate))))
+            out = np.empty((rows, self.K), np.float64)
+        check(self._lib.mbar_b200_log_W_nk_rows(self._h, _dptr(f), int(row0), rows, C.c_void_p(out.ctypes.data),
+                                                out.strides[0] // 8, int(bool(exponentiate))))
         return out
 
     def log_denominator(self, f_k):
         f = _f64(f_k, self.K)
+        if self._bad(f):                 # the reference propagates NaN (ADVICE r1)
+            return np.full(self.N, np.nan)
         out = np.empty(self.N)
         check(self._lib.mbar_b200_log_denominator(self._h, _dptr(f), _dptr(out)))
         return out

@@ -1,0 +1,193 @@
+"""Round-2 kernels through the C ABI: device-resident solver loops (mbar_solvers.py:510-667 adaptive,
+self-consistent iteration), the on-device Newton step (Cholesky of H[1:,1:]), the candidate-batched pass and the
+three Hessian kernel paths (mbar_solvers.py:395-411), against the oracle / the reference-generated fixtures and
+against the host-stepped loops of round 1."""
+import numpy as np
+import pytest
+
+from oracle import mbar_oracle as orc
+from oracle import testsystems as ots
+from tests import _cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import pymbar_b200
+    from pymbar_b200 import _lib
+
+    _lib.load()
+    if _lib.device_count() == 0:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box")
+    return pymbar_b200
+
+
+@pytest.mark.parametrize("batch", [1, 4])
+@pytest.mark.parametrize("name", _cases.ALL)
+def test_adaptive_device_resident_vs_reference_and_stepped(lib, name, batch):
+    z = _cases.load(name)
+    u, N = z["u_kn"], z["N_k"].astype(float)
+    s = N > 0
+    K = len(N)
+    ref = np.zeros(K)
+    ref[s] = z["adaptive_x"]
+    with lib.DeviceProblem(u, N) as p:
+        p.set_loop_mode("device", batch)
+        polls0 = p.loop_stats()["polls"]
+        f_dev, r = p.solve_adaptive(np.zeros(K), tol=1e-12, min_sc_iter=0)
+        polls = p.loop_stats()["polls"] - polls0
+        assert r["success"], r
+        assert np.max(np.abs(f_dev[s] - ref[s])) < 1e-8                    # reference adaptive() solution
+        assert r["iterations"] == r["nr_iterations"] + r["sci_iterations"]
+        # no per-iteration host round trip: one poll per batch of iterations
+        assert polls <= -(-r["iterations"] // batch) + 1, (polls, r)
+        p.set_loop_mode("stepped")
+        f_st, r2 = p.solve_adaptive(np.zeros(K), tol=1e-12, min_sc_iter=0)
+        assert r2["success"]
+        assert np.max(np.abs(f_dev[s] - f_st[s])) < 1e-9
+        # gradient norm reported by the device loop is the real one at the returned point
+        g = p.gradient(f_dev)
+        assert abs(np.linalg.norm(g) - r["gnorm"]) < 1e-7 * N.max()
+
+
+@pytest.mark.parametrize("name", ["small_osc_8x40", "small_empty_state", "osc_50x100"])
+def test_sci_device_resident(lib, name):
+    z = _cases.load(name)
+    u, N = z["u_kn"], z["N_k"].astype(float)
+    s = N > 0
+    K = len(N)
+    ref = np.zeros(K)
+    ref[s] = z["adaptive_x"]
+    with lib.DeviceProblem(u, N) as p:
+        p.set_loop_mode("device", 8)
+        polls0 = p.loop_stats()["polls"]
+        f_dev, r = p.solve_sci(np.zeros(K), tol=1e-12, maxiter=50000)
+        polls = p.loop_stats()["polls"] - polls0
+        assert r["success"] and np.max(np.abs(f_dev[s] - ref[s])) < 1e-7, r
+        assert polls <= -(-r["iterations"] // 8) + 1
+        p.set_loop_mode("stepped")
+        f_st, r2 = p.solve_sci(np.zeros(K), tol=1e-12, maxiter=50000)
+        assert r2["success"] and abs(r2["iterations"] - r["iterations"]) <= 2
+        assert np.max(np.abs(f_dev[s] - f_st[s])) < 1e-10
+        # maxiter is honoured exactly by the device loop
+        p.set_loop_mode("device", 4)
+        f7, r7 = p.solve_sci(np.zeros(K), tol=1e-30, maxiter=7)
+        assert r7["iterations"] == 7 and not r7["success"]
+        f_host = np.zeros(K)
+        for _ in range(7):
+            nxt = orc.self_consistent_update(u[s], N[s], f_host[s])
+            f_host[s] = nxt - nxt[0]
+        np.testing.assert_allclose(f7[s], f_host[s], atol=1e-11)
+
+
+def _random_problem(K, N, seed, empty=()):
+    u, N_k = ots.oscillators(K, max(1, N // K), seed=seed)
+    N_k = N_k.astype(float)
+    for e in empty:
+        N_k[e] = 0.0
+    rng = np.random.RandomState(seed)
+    f = rng.normal(scale=0.5, size=K)
+    f -= f[0]
+    return u, N_k, f
+
+
+@pytest.mark.parametrize("K", [2, 5, 16, 17, 32, 33, 48, 64, 65, 96, 128, 129, 200, 256, 300, 384])
+def test_hessian_kernel_paths_vs_oracle(lib, K):
+    """K <= 64: warp-per-tile kernel (KT = 2, 4, 8); K > 64: materialised weights + 128 x 128 block pairs with
+    partial last blocks; unsampled states anywhere."""
+    empty = () if K < 5 else (1, K - 2)
+    u, N_k, f = _random_problem(K, 37 * K if K < 100 else 12 * K, seed=K, empty=empty)
+    s = N_k > 0
+    with lib.DeviceProblem(u, N_k) as p:
+        H = p.hessian(f)
+        H_ref = orc.mbar_hessian(u[s], N_k[s], f[s])
+        scale = np.max(np.abs(H_ref))
+        np.testing.assert_allclose(H[np.ix_(s, s)], H_ref, rtol=1e-10, atol=1e-11 * scale)
+        assert np.all(H[~s] == 0) and np.all(H[:, ~s] == 0)
+        np.testing.assert_allclose(H, H.T, rtol=0, atol=0)
+        names = p.last_kernels()
+        assert ("hessian_small_kernel" in names["hessian_kernel"]) == (K <= 64), names
+        # all states (weight moments): unsampled rows switched on
+        S, G = p.weight_moments(f)
+        W = orc.mbar_W_nk(u, N_k, f)
+        np.testing.assert_allclose(G, W.T @ W, rtol=1e-9, atol=1e-13 * np.max(W.T @ W))
+
+
+def test_hessian_weighted_samples(lib):
+    """bootstrap multiplicities enter the second moments as sqrt(w_n) on both factors"""
+    for K in (24, 130):
+        u, N_k, f = _random_problem(K, 40 * K, seed=3 + K)
+        rng = np.random.RandomState(5)
+        w = rng.poisson(1.0, size=u.shape[1]).astype(float)
+        with lib.DeviceProblem(u, N_k) as p:
+            p.set_sample_weights(w)
+            _, _, G = p.streaming_pass(f, want_G=True)
+            W = orc.mbar_W_nk(u, N_k, f)
+            np.testing.assert_allclose(G, (W * w[:, None]).T @ W, rtol=1e-9, atol=1e-16)
+
+
+@pytest.mark.parametrize("K", [3, 40, 161, 200, 320])
+def test_device_newton_step_sizes(lib, K):
+    """Cholesky + triangular solves on the device: shared-memory variant (n <= 160) and the L2-resident one;
+    one adaptive iteration from f = 0 must reproduce the oracle's first iterate."""
+    u, N_k, _ = _random_problem(K, 30 * K, seed=100 + K)
+    with lib.DeviceProblem(u, N_k) as p:
+        p.set_loop_mode("device", 1)
+        f1, r = p.solve_adaptive(np.zeros(K), tol=1e-12, maxiter=1, min_sc_iter=0)
+        assert r["iterations"] == 1
+        ref = orc.adaptive(u, N_k, np.zeros(K), tol=1e-12, options=dict(maxiter=1, min_sc_iter=0))["x"]
+        np.testing.assert_allclose(f1, ref, atol=5e-9)
+        f_dev, r = p.solve_adaptive(np.zeros(K), tol=1e-12, min_sc_iter=0)
+        assert r["success"] and r["nr_iterations"] >= 1
+        g = orc.mbar_gradient(u, N_k, f_dev)
+        assert np.max(np.abs(g)) < 1e-7 * N_k.max()
+
+
+def test_pass_multi(lib):
+    z = _cases.load("osc_50x100")
+    u, N = z["u_kn"], z["N_k"].astype(float)
+    K = len(N)
+    rng = np.random.RandomState(1)
+    f2 = np.stack([z["f_rand"], z["f_rand"] + rng.normal(scale=0.1, size=K)])
+    with lib.DeviceProblem(u, N) as p:
+        S, sumL = p.pass_multi(f2)
+        for m in range(2):
+            S1, sumL1, _ = p.streaming_pass(f2[m])
+            np.testing.assert_allclose(S[m], S1, rtol=1e-13)
+            np.testing.assert_allclose(sumL[m], sumL1, rtol=1e-14)
+            S_ref, L_ref = orc.single_pass_sums(u, N, f2[m])
+            np.testing.assert_allclose(S[m], S_ref, rtol=1e-11)
+        # wildly different candidates (fused range flag -> robust path) still answer correctly
+        f_far = np.stack([z["f_rand"], np.linspace(0, 900, K)])
+        S, sumL = p.pass_multi(f_far)
+        S_ref, L_ref = orc.single_pass_sums(u, N, f_far[1])
+        np.testing.assert_allclose(sumL[1], L_ref.sum(), rtol=1e-12)
+
+
+def test_device_loop_falls_back_on_extreme_start(lib):
+    """A start hundreds of kT from self-consistency underflows the linear-domain sums of the fused kernel: the
+    device loop must hand over to the robust stepped path and still converge to the reference solution."""
+    z = _cases.load("small_osc_8x40")
+    u, N = z["u_kn"], z["N_k"].astype(float)
+    K = len(N)
+    f0 = np.linspace(0.0, 700.0, K)
+    with lib.DeviceProblem(u, N) as p:
+        f, r = p.solve_adaptive(f0, tol=1e-12, min_sc_iter=0)
+        assert r["success"] and np.max(np.abs(f - z["adaptive_x"])) < 1e-8
+        f, r = p.solve_sci(f0, tol=1e-13, maxiter=100000)
+        assert r["success"] and np.max(np.abs(f - z["adaptive_x"])) < 1e-7
+
+
+def test_fp64_peak_probe_and_kernel_names(lib):
+    from pymbar_b200.problem import measure_fp64_peak
+
+    dmma, dfma = measure_fp64_peak(0)
+    assert 15.0 < dmma < 80.0 and 15.0 < dfma < 80.0, (dmma, dfma)
+    z = _cases.load("osc_50x100")
+    with lib.DeviceProblem(z["u_kn"], z["N_k"].astype(float)) as p:
+        p.gradient(z["f_rand"])
+        assert "pass_fused_kernel<" in p.last_kernels()["pass_kernel"]
+        p.set_kernel("generic")
+        p.gradient(z["f_rand"])
+        assert "pass_generic_kernel<" in p.last_kernels()["pass_kernel"]
