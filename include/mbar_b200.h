@@ -88,6 +88,11 @@ int mbar_b200_device_count(int* count);
 int mbar_b200_host_alloc(void** ptr, uint64_t bytes);
 int mbar_b200_host_free(void* ptr);
 
+/* 64-bit content hash of a host matrix of `rows` rows of `row_bytes` bytes, row stride `stride_bytes` (threaded,
+ * memory-bandwidth bound, independent of the thread count).  A binding that keeps u_kn resident between the
+ * reference's pure-function calls keys its cache on this, never on a sample of the contents. */
+int mbar_b200_host_hash(const void* base, int64_t rows, int64_t row_bytes, int64_t stride_bytes, uint64_t* hash_out);
+
 /* Release the buffers parked by destroyed contexts (at most one u_kn-sized device buffer and one staging set
  * per device are kept for the next context; MBAR_B200_NO_POOL=1 in the environment disables the parking). */
 int mbar_b200_trim(void);

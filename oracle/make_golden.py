@@ -148,8 +148,32 @@ def case(name, u_kn, N_k, store_u, regen, rng):
           f"fk_default[:4]={data['fk_default'][:4]}")
 
 
+def c1_case():
+    """BASELINE.json configs[0] (C1): HarmonicOscillatorsTestCase() defaults, K=5, N_k=[1000]*5, seed 0
+    (SURVEY.md 8d).  Separate RNG stream so the older fixtures stay byte-identical; also pins
+    precondition_u_kn (mbar_solvers.py:710-735, row a6) through probes of its output."""
+    rng = np.random.RandomState(4321)
+    O, Kk, Nk = [0.0, 1.0, 2.0, 3.0, 4.0], [1.0, 2.0, 4.0, 8.0, 16.0], [1000] * 5
+    u, N = ref_harmonic(O, Kk, Nk, 0)
+    _, u2, _ = ots.harmonic_u_kn(O, Kk, Nk, seed=0)
+    assert np.array_equal(u, u2), "restated harmonic sampler is not bit-exact"
+    case("c1_harmonic_5x1000", u, N, store_u=False, regen=("harmonic", O, Kk, Nk, 0), rng=rng)
+    path = os.path.join(OUT, "c1_harmonic_5x1000.npz")
+    data = dict(np.load(path, allow_pickle=False))
+    Nf = 1.0 * np.asarray(N)
+    for tag, f in (("zero", np.zeros(5)), ("rand", data["f_rand"])):
+        pc = ref.precondition_u_kn(u, Nf, f)
+        data[f"{tag}_precond_head"] = pc[:, :64].copy()
+        data[f"{tag}_precond_rowsum"] = pc.sum(1)
+        data[f"{tag}_precond_obj"] = np.float64(ref.mbar_objective(pc, Nf, f))
+    np.savez_compressed(path, **data)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--only-c1" in sys.argv:
+        c1_case()
+        return
     rng = np.random.RandomState(1234)
 
     # --- the reference's literal golden vector ---------------------------------------------
@@ -195,6 +219,7 @@ def main():
             u2, _ = ots.exponentials(ks, ns, seed=seed)
         assert np.array_equal(u, u2), "restated sampler is not bit-exact"
         case(f"{kind}_{ks}x{ns}", u, N, False, (kind, ks, ns, seed), rng)
+    c1_case()
 
 
 if __name__ == "__main__":

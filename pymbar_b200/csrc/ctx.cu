@@ -370,6 +370,62 @@ int mbar_b200_host_free(void* ptr) {
     return MBAR_B200_OK;
 }
 
+// 64-bit content hash of a strided host matrix (rows x row_bytes, row stride stride_bytes), computed by several
+// threads at memory bandwidth: the residency cache of the Python mirror keys on it, so that an in-place edit of
+// u_kn between two calls can never be served from the stale device copy (a sampled probe could miss it).
+static inline uint64_t mix64(uint64_t h, uint64_t w) {
+    h ^= w;
+    h *= 0x9E3779B97F4A7C15ull;
+    return h ^ (h >> 29);
+}
+static uint64_t hash_span(const unsigned char* p, size_t bytes, uint64_t seed) {
+    uint64_t h0 = seed, h1 = seed ^ 0xD6E8FEB86659FD93ull, h2 = seed + 0xA0761D6478BD642Full, h3 = ~seed;
+    size_t i = 0;
+    for (; i + 32 <= bytes; i += 32) {        // four independent lanes: the multiply chains overlap
+        uint64_t w[4];
+        std::memcpy(w, p + i, 32);
+        h0 = mix64(h0, w[0]);
+        h1 = mix64(h1, w[1]);
+        h2 = mix64(h2, w[2]);
+        h3 = mix64(h3, w[3]);
+    }
+    for (; i < bytes; ++i) h0 = mix64(h0, p[i]);
+    return mix64(mix64(mix64(h0, h1), h2), h3);
+}
+
+int mbar_b200_host_hash(const void* base, int64_t rows, int64_t row_bytes, int64_t stride_bytes, uint64_t* out) {
+    MBAR_REQUIRE(base && out && rows >= 0 && row_bytes >= 0 && stride_bytes >= row_bytes, MBAR_B200_ERR_INVALID,
+                 "bad argument");
+    const unsigned char* b = static_cast<const unsigned char*>(base);
+    // split every row into fixed 4 MiB blocks; block hashes are combined in block order (thread-count independent)
+    const int64_t blk = 4ll << 20;
+    const int64_t perRow = row_bytes ? (row_bytes + blk - 1) / blk : 0;
+    const int64_t nBlocks = rows * perRow;
+    std::vector<uint64_t> part((size_t)nBlocks);
+    int nthr = (int)std::min<int64_t>(16, std::max<int64_t>(1, nBlocks));
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && nthr > hw) nthr = hw;
+    auto work = [&](int t) {
+        for (int64_t i = t; i < nBlocks; i += nthr) {
+            const int64_t r = i / perRow, c = i % perRow;
+            const int64_t off = c * blk, len = std::min(blk, row_bytes - off);
+            part[(size_t)i] = hash_span(b + r * stride_bytes + off, (size_t)len, 0x243F6A8885A308D3ull + (uint64_t)i);
+        }
+    };
+    if (nthr == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthr; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+    uint64_t h = 0x13198A2E03707344ull ^ (uint64_t)rows ^ ((uint64_t)row_bytes << 20);
+    for (uint64_t v : part) h = mix64(h, v);
+    *out = h;
+    return MBAR_B200_OK;
+}
+
 int mbar_b200_create(mbar_b200_ctx** out, int device, int32_t K, int64_t N_local, const double* N_k) {
     MBAR_REQUIRE(out && N_k, MBAR_B200_ERR_INVALID, "NULL argument");
     *out = nullptr;

@@ -9,14 +9,19 @@ compiled library and a B200 every call raises.
 Residency.  The reference functions are pure functions of host arrays.  Re-uploading u_kn for
 every call would turn a 3 ms pass into a PCIe transfer, so calls are served from a small cache of
 :class:`DeviceProblem` objects keyed on the identity (address, shape, strides), the N_k vector and
-a strided content fingerprint of u_kn.  ``PYMBAR_B200_CACHE=0`` disables the cache (every call
-uploads).  The drivers (``solve_mbar*``) hold one problem explicitly for the whole protocol.
+a 64-bit hash of the WHOLE array (``mbar_b200_host_hash``: threaded, memory-bandwidth bound, far
+cheaper than the upload it saves) — an in-place edit of u_kn can therefore never be answered from a
+stale device copy.  Entries die with their host array (weakref) or through :func:`invalidate` /
+:func:`clear_cache`; ``PYMBAR_B200_CACHE=0`` disables the cache (every call uploads).  The drivers
+(``solve_mbar*``) hold one problem explicitly for the whole protocol.
 """
 from __future__ import annotations
 
+import ctypes
 import logging
 import os
 import warnings
+import weakref
 from collections import OrderedDict
 
 import numpy as np
@@ -64,12 +69,18 @@ def _cache_enabled():
     return os.environ.get("PYMBAR_B200_CACHE", "1").lower() not in ("0", "false", "no")
 
 
-def _fingerprint(u_kn):
-    """Content probe of ~4096 evenly spaced entries (no copy of the array, whatever its strides)."""
+def _content_hash(u_kn):
+    """Exact-content key: 64-bit hash of every byte of the (possibly row-strided) array."""
+    from . import _lib
+
     if u_kn.size == 0:
         return 0
-    idx = np.linspace(0, u_kn.size - 1, num=min(4096, u_kn.size)).astype(np.int64)
-    return hash(np.asarray(u_kn.flat[idx]).tobytes())
+    if u_kn.ndim != 2 or u_kn.strides[1] != u_kn.itemsize or u_kn.strides[0] < u_kn.shape[1] * u_kn.itemsize:
+        u_kn = np.ascontiguousarray(u_kn)
+    h = ctypes.c_uint64(0)
+    _lib.check(_lib.load().mbar_b200_host_hash(ctypes.c_void_p(u_kn.ctypes.data), u_kn.shape[0],
+                                               u_kn.shape[1] * u_kn.itemsize, u_kn.strides[0], ctypes.byref(h)))
+    return h.value
 
 
 def clear_cache():
@@ -78,16 +89,40 @@ def clear_cache():
         p.close()
 
 
+def invalidate(u_kn=None):
+    """Drop the cached device copies of `u_kn` (or all of them)."""
+    if u_kn is None:
+        return clear_cache()
+    addr = np.asarray(u_kn).__array_interface__["data"][0]
+    for key in [k for k in _CACHE if k[0] == addr]:
+        _CACHE.pop(key).close()
+
+
+def _evict(key):
+    prob = _CACHE.pop(key, None)
+    if prob is not None:
+        prob.close()
+
+
 def _problem_for(u_kn, N_k):
-    """DeviceProblem holding (u_kn, N_k), from the cache when the same host array is seen again."""
+    """DeviceProblem holding (u_kn, N_k), from the cache when the same host array WITH THE SAME CONTENTS is
+    seen again."""
     if not _cache_enabled():
         return DeviceProblem(u_kn, N_k, device=_DEVICE), False
     key = (u_kn.__array_interface__["data"][0], u_kn.shape, u_kn.strides,
-           np.asarray(N_k, np.float64).tobytes(), _fingerprint(u_kn))
+           np.asarray(N_k, np.float64).tobytes(), _content_hash(u_kn))
     prob = _CACHE.get(key)
     if prob is None:
+        # a different content at the same address supersedes the old entry (the caller edited in place)
+        for stale in [k for k in _CACHE if k[:3] == key[:3]]:
+            _CACHE.pop(stale).close()
         prob = DeviceProblem(u_kn, N_k, device=_DEVICE)
         _CACHE[key] = prob
+        try:
+            # the device copy must not outlive the host array it mirrors
+            prob._host_ref = weakref.ref(u_kn, lambda _r, key=key: _evict(key))
+        except TypeError:
+            pass
         while len(_CACHE) > _CACHE_SLOTS:
             _, old = _CACHE.popitem(last=False)
             old.close()

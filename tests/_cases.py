@@ -11,7 +11,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 SMALL = ["small_osc_8x40", "small_exp_6x50", "small_empty_state", "small_empty_first"]
 MEDIUM = ["osc_50x100", "osc_100x100", "osc_200x50", "exp_200x50"]
-ALL = ["golden_example"] + SMALL + MEDIUM
+C1 = ["c1_harmonic_5x1000"]     # BASELINE.json configs[0]: HarmonicOscillatorsTestCase() defaults, K=5, N=5000
+ALL = ["golden_example"] + SMALL + MEDIUM + C1
 
 
 def _regen(spec):

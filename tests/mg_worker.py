@@ -51,6 +51,20 @@ def main():
         f5p = p.sci_iterate(np.zeros(len(N)), 5)         # in-kernel exchange over peer memory
         f5p = p.sci_iterate(f5p, 0)
         errs_peer = np.max(np.abs(f5p[s] - f5[s]))
+        # device-resident loops over the peer exchange (every pass of the adaptive iteration exchanges in-kernel,
+        # the K x K Hessian goes through NCCL) and host-stepped loops must agree with the NCCL-only run above
+        fk_p, r_p = p.solve_adaptive(np.zeros(len(N)), tol=1e-12, min_sc_iter=0)
+        errs["adaptive_peer"] = np.max(np.abs(fk_p[s] - ref[s]))
+        assert r_p["success"] and r["success"], (r, r_p)
+        p.set_loop_mode("stepped")
+        fk_s, r_s = p.solve_adaptive(np.zeros(len(N)), tol=1e-12, min_sc_iter=0)
+        p.set_loop_mode("device")
+        errs["adaptive_stepped_vs_device"] = np.max(np.abs(fk_s[s] - fk_p[s]))
+        fs_p, rs_p = p.solve_sci(np.zeros(len(N)), tol=1e-11, maxiter=20000)
+        errs["sci_loop_peer"] = np.max(np.abs(fs_p[s] - ref[s])) * 1e-2       # SCI stops ~1e-9 from the optimum
+        gb = [None] * world
+        dist.all_gather_object(gb, (fk_p.tobytes(), fs_p.tobytes(), fk.tobytes()))
+        assert all(b == gb[0] for b in gb), "ranks disagree after the device-resident loops"
         fh = np.zeros(len(N))
         for _ in range(5):
             nxt = orc.self_consistent_update(u[s], N[s], fh[s])
@@ -67,7 +81,8 @@ def main():
         p.close()
     dist.barrier()
     if rank == 0:
-        print(f"MG_OK world={world} worst_err={worst:.3e}")
+        print(f"MG_OK world={world} worst_err={worst:.3e} (primitives, NCCL + in-kernel peer exchange, "
+              f"device-resident and host-stepped loops; bit-identical f on all ranks)")
     dist.destroy_process_group()
 
 

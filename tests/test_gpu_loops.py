@@ -191,3 +191,33 @@ def test_fp64_peak_probe_and_kernel_names(lib):
         p.set_kernel("generic")
         p.gradient(z["f_rand"])
         assert "pass_generic_kernel<" in p.last_kernels()["pass_kernel"]
+
+
+def test_precondition_u_kn_and_c1_on_gpu(lib):
+    """Row a6 (precondition_u_kn, mbar_solvers.py:710-735) through the mirror on the GPU vs probes of the
+    reference's output, on BASELINE config C1 (HarmonicOscillatorsTestCase defaults, K=5, N=5000)."""
+    z = _cases.load("c1_harmonic_5x1000")
+    u, N = z["u_kn"], z["N_k"]
+    ms = lib.mbar_solvers
+    for tag, f in (("zero", np.zeros(5)), ("rand", z["f_rand"])):
+        pc = ms.precondition_u_kn(u, N, f)
+        assert pc.shape == u.shape and pc.flags.writeable
+        np.testing.assert_allclose(pc[:, :64], z[f"{tag}_precond_head"], rtol=0, atol=1e-11)
+        np.testing.assert_allclose(pc.sum(1), z[f"{tag}_precond_rowsum"], rtol=1e-12)
+        # the preconditioned objective is ~0 at f (what the shift is for, mbar_solvers.py:726-734)
+        np.testing.assert_allclose(ms.mbar_objective(pc, N, f), z[f"{tag}_precond_obj"], atol=1e-7)
+    ms.clear_cache()
+
+
+@pytest.mark.parametrize("method", ["lm", "BFGS", "Newton-CG", "trust-ncg", "dogleg", "CG"])
+def test_scipy_methods_against_the_device(lib, method):
+    """solve_mbar_once (mbar_solvers.py:738-883) hands device closures (gradient / Hessian / objective) to
+    scipy.optimize.root / minimize for every method family of mbar_solvers.py:120-139."""
+    z = _cases.load("small_osc_8x40")
+    ms = lib.mbar_solvers
+    u, N = z["u_kn"], z["N_k"].astype(float)
+    f, results = ms.solve_mbar_once(u, N, np.zeros(len(N)), method=method, tol=1e-12)
+    f_ref, _ = orc.solve_mbar_once(u, N, np.zeros(len(N)), method=method, tol=1e-12)
+    assert np.max(np.abs(f - f_ref)) < 1e-7
+    assert np.max(np.abs(f - z["fk_default"])) < 1e-6
+    ms.clear_cache()

@@ -59,3 +59,15 @@ def test_single_pass_formulation(name):
     np.testing.assert_allclose(f - np.log(S), orc.self_consistent_update(u, N, f), atol=1e-12)
     np.testing.assert_allclose(N * (S - 1), orc.mbar_gradient(u, N, f), rtol=1e-11, atol=1e-10)
     np.testing.assert_allclose(L.sum() - N @ f, orc.mbar_objective(u, N, f), rtol=1e-13)
+
+
+def test_c1_precondition_matches_reference():
+    """precondition_u_kn (mbar_solvers.py:710-735) of the oracle vs probes of the reference's
+    output on BASELINE config C1; the C1 solve itself is part of the parametrised tests above."""
+    z = _cases.load("c1_harmonic_5x1000")
+    u, N = z["u_kn"], z["N_k"].astype(float)
+    for tag, f in (("zero", np.zeros(5)), ("rand", z["f_rand"])):
+        pc = orc.precondition_u_kn(u, N, f)
+        np.testing.assert_allclose(pc[:, :64], z[f"{tag}_precond_head"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(pc.sum(1), z[f"{tag}_precond_rowsum"], rtol=1e-13)
+        np.testing.assert_allclose(orc.mbar_objective(pc, N, f), z[f"{tag}_precond_obj"], atol=1e-8)
