@@ -557,6 +557,12 @@ def e2e_legs(rig, args, prob, K, N_local, N_k):
                    "collective in this leg)") if rig.distributed else "single GPU"
     e2e["pageable_source"] = res.get("pageable")
     e2e["pcie_note"] = "fraction of 63 GB/s (PCIe Gen5 x16 payload ceiling); the step is the 20.48 GB upload"
+    try:
+        from pymbar_b200.problem import gpu_numa_node
+
+        e2e["gpu_numa_node"] = gpu_numa_node(rig.local)      # pinned staging is allocated with this node preferred
+    except Exception:  # pragma: no cover
+        pass
     # ---- e2e_solve: the two calls of MBAR.__init__ on a pageable array, itemised ---------------------
     e2e_solve = None
     if args.e2e_solve and not rig.distributed:

@@ -87,6 +87,9 @@ int mbar_b200_device_count(int* count);
 /* Pinned host memory for zero-staging uploads/downloads (cudaHostAlloc / cudaFreeHost). */
 int mbar_b200_host_alloc(void** ptr, uint64_t bytes);
 int mbar_b200_host_free(void* ptr);
+/* NUMA node the GPU hangs off (sysfs), -1 when the host exposes none.  Pinned staging buffers are allocated with
+ * that node preferred so uploads / downloads do not cross the inter-socket link. */
+int mbar_b200_gpu_numa_node(int device, int* node);
 
 /* 64-bit content hash of a host matrix of `rows` rows of `row_bytes` bytes, row stride `stride_bytes` (threaded,
  * memory-bandwidth bound, independent of the thread count).  A binding that keeps u_kn resident between the

@@ -44,6 +44,7 @@ SIGNATURES = {
     "mbar_b200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "mbar_b200_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     "mbar_b200_host_free": (C.c_int, [C.c_void_p]),
+    "mbar_b200_gpu_numa_node": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     "mbar_b200_host_hash": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]),
     "mbar_b200_trim": (C.c_int, []),
     "mbar_b200_create": (C.c_int, [C.POINTER(_ctx), C.c_int, C.c_int32, C.c_int64, _dp]),

@@ -210,6 +210,14 @@ struct NvtxRange {
     ~NvtxRange();
 };
 
+// Prefer the GPU's NUMA node for host allocations made while this object lives (ctx.cu).
+int gpu_numa_node(int device);
+struct NumaPrefer {
+    bool active = false;
+    explicit NumaPrefer(int device);
+    ~NumaPrefer();
+};
+
 // ---- host-side helpers implemented across the .cu files ----
 int check_range(mbar_b200_ctx* c, const double* f);
 int run_pass(mbar_b200_ctx* c, const double* f, PassWant want);   // pass + all-reduce + D2H into ctx->h_out

@@ -70,7 +70,10 @@ int launch_logw(mbar_b200_ctx* ctx, const double* h_f, double* logW_host, int64_
     const size_t chunkBytes = (size_t)tilesPerChunk * TILE_N * K * sizeof(double);
     for (int i = 0; i < 2; ++i) {
         MBAR_CUDA(cudaMalloc((void**)&d_out[i], chunkBytes));
-        if (!pinnedDst) MBAR_CUDA(cudaHostAlloc((void**)&h_stage[i], chunkBytes, cudaHostAllocDefault));
+        if (!pinnedDst) {
+            NumaPrefer numa(ctx->device);
+            MBAR_CUDA(cudaHostAlloc((void**)&h_stage[i], chunkBytes, cudaHostAllocDefault));
+        }
     }
     int rc = MBAR_B200_OK;
     cudaEvent_t done[2];

@@ -327,3 +327,10 @@ def measure_fp64_peak(device=0):
     a, b = C.c_double(0), C.c_double(0)
     check(_lib.load().mbar_b200_measure_fp64_peak(int(device), C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def gpu_numa_node(device=0):
+    """NUMA node of the GPU's PCI function (-1: the host exposes none)."""
+    n = C.c_int(-1)
+    check(_lib.load().mbar_b200_gpu_numa_node(int(device), C.byref(n)))
+    return n.value
