@@ -119,6 +119,12 @@ int mbar_b200_last_pass_ms(mbar_b200_ctx* ctx, double* ms);
 int mbar_b200_upload_u_kn(mbar_b200_ctx* ctx, const double* u_host, int64_t ld);
 /* Same, from a row-major DEVICE buffer on ctx's device (e.g. a torch tensor's data_ptr). */
 int mbar_b200_upload_u_kn_dev(mbar_b200_ctx* ctx, const double* u_dev, int64_t ld);
+/* A new context holding the samples of `base` plus n_extra UNSAMPLED states whose energies are u_extra_host
+ * [n_extra, N_local] (row stride ld).  The resident tiles are copied device-to-device; only the new rows cross
+ * PCIe.  This is how expectations / perturbed free energies (the columns mbar.py:886-940 appends to Log_W_nk)
+ * reuse the resident u_kn.  `base` stays valid and independent. */
+int mbar_b200_create_augmented(mbar_b200_ctx* base, int32_t n_extra, const double* u_extra_host, int64_t ld,
+                               mbar_b200_ctx** ctx_out);
 /* Fill the context on device from the synthetic family (no host traffic). */
 int mbar_b200_synthesize(mbar_b200_ctx* ctx, const mbar_b200_synth* spec);
 /* Per-sample multiplicities w_n >= 0 ([N_local] host doubles; NULL restores w_n = 1).  Every sum over

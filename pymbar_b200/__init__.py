@@ -24,7 +24,7 @@ _PATCHED = (
 )
 
 
-def install(target=None, patch_layout_helpers=True):
+def install(target=None, patch_layout_helpers=True, patch_mbar=True):
     """Route ``pymbar.mbar_solvers`` (or `target`, a module object) through the B200 backend.
 
     pymbar looks its solver entry points up as module attributes at call time (mbar.py:413, :437,
@@ -63,10 +63,21 @@ def install(target=None, patch_layout_helpers=True):
                 if (mbar_mod, name) not in _SAVED:
                     _SAVED[(mbar_mod, name)] = getattr(mbar_mod, name)
                 setattr(mbar_mod, name, getattr(u, name))
+    if patch_mbar and target.__name__ == "pymbar.mbar_solvers":
+        # lazy Log_W_nk + estimators / expectations from device moments (see facade.py)
+        import pymbar.mbar as mbar_mod
+
+        from . import facade
+
+        facade.install_on(mbar_mod.MBAR)
     return target
 
 
 def uninstall():
+    from . import facade
+
+    for cls in list(facade._SAVED):
+        facade.uninstall_from(cls)
     for key, fn in list(_SAVED.items()):
         if key == ("ParameterError",):
             from . import mbar_solvers as backend

@@ -55,6 +55,7 @@ SIGNATURES = {
     "mbar_b200_last_pass_ms": (C.c_int, [_ctx, _dp]),
     "mbar_b200_upload_u_kn": (C.c_int, [_ctx, C.c_void_p, C.c_int64]),
     "mbar_b200_upload_u_kn_dev": (C.c_int, [_ctx, C.c_void_p, C.c_int64]),
+    "mbar_b200_create_augmented": (C.c_int, [_ctx, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(_ctx)]),
     "mbar_b200_synthesize": (C.c_int, [_ctx, C.POINTER(Synth)]),
     "mbar_b200_set_sample_weights": (C.c_int, [_ctx, C.c_void_p]),
     "mbar_b200_download_u_kn": (C.c_int, [_ctx, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),

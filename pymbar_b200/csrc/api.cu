@@ -135,12 +135,13 @@ int run_pass(mbar_b200_ctx* c, const double* f, PassWant want) {
     // attempt 0: fused (if applicable) | 1: generic, linear sums | 2: generic, log-domain sums for
     // every state (the reference's second logsumexp, mbar_solvers.py:240): taken when a sampled
     // state's S_k underflows, i.e. f_k is hundreds of kT away from self-consistency.
-    bool fused = false;
+    bool fused = false, wroteW = false;
     for (int attempt = 0; attempt < 3; ++attempt) {
         fused = false;
+        wroteW = false;
         const bool logAll = (attempt == 2);
         if (attempt == 0 && c->kernelChoice != MBAR_B200_KERNEL_GENERIC)
-            MBAR_TRY(launch_pass_fused(c, f, wantL, needUnsampled, &fused));
+            MBAR_TRY(launch_pass_fused(c, f, wantL, needUnsampled, &fused, want.G && !want.Gall, &wroteW));
         if (attempt == 0 && !fused) continue;
         if (!fused) MBAR_TRY(launch_pass_generic(c, f, wantL, logAll));
         // S | sumL | flag are sums over samples -> one all-reduce
@@ -193,7 +194,7 @@ int run_pass(mbar_b200_ctx* c, const double* f, PassWant want) {
     }
     if (want.G || want.Gall) {
         NvtxRange nvtxH("mbar_b200::hessian");
-        MBAR_TRY(launch_hessian(c, f, want.Gall));
+        MBAR_TRY(launch_hessian(c, f, want.Gall, fused && wroteW));
         MBAR_TRY(comm_allreduce(c, c->d_out + lay.G(), K * K, 0));
         MBAR_CUDA(cudaMemcpyAsync(c->h_out + lay.G(), c->d_out + lay.G(), (size_t)K * K * sizeof(double),
                                   cudaMemcpyDeviceToHost, c->stream));

@@ -818,6 +818,159 @@ int mbar_b200_upload_u_kn(mbar_b200_ctx* c, const double* u_host, int64_t ld) {
     return finish_upload(c);
 }
 
+// ------------------------------------------------------------------------------------------
+// Appended (unsampled) states on top of a resident problem.
+// Every column the reference appends to Log_W_nk for an expectation or a perturbed free energy
+// (mbar.py:886-940) is an unsampled state of an augmented problem with the SAME samples.  Instead of uploading
+// the augmented (K + E) x N matrix again, the resident tiles are copied device-to-device into the wider tile
+// stride and only the E new rows cross PCIe.  The per-sample shift x_n (min over SAMPLED states) is unchanged.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) widen_tiles_kernel(const double* __restrict__ src, int K, int Knew,
+                                                          int64_t nTiles, double* __restrict__ dst) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        const double* s = src + tile * (int64_t)K * TILE_N + lane;
+        double* d = dst + tile * (int64_t)Knew * TILE_N + lane;
+#pragma unroll 4
+        for (int k = warp; k < K; k += 8) d[(int64_t)k * TILE_N] = s[(int64_t)k * TILE_N];
+    }
+}
+// rows [K, K + E) of tiles [tile0, tile0 + nT) from a row-major staging block [E, ldCols]
+__global__ void __launch_bounds__(256) append_rows_kernel(const double* __restrict__ stage, int64_t ldCols, int E,
+                                                          int K, int Knew, int64_t tile0, int64_t validCols,
+                                                          const double* __restrict__ xshift,
+                                                          double* __restrict__ dst, int* __restrict__ flags) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tl = blockIdx.x;
+    const int64_t col = tl * TILE_N + lane;
+    const bool valid = col < validCols;
+    const double x = xshift[(tile0 + tl) * TILE_N + lane];
+    double* out = dst + (tile0 + tl) * (int64_t)Knew * TILE_N + (int64_t)K * TILE_N + lane;
+    int bad = 0, extreme = 0;
+    for (int r = warp; r < E; r += 8) {
+        double v = valid ? stage[(int64_t)r * ldCols + col] : 0.0;
+        if (v != v) bad = 1;
+        v = fmin(v - x, U_CLAMP);
+        if (valid && v < -1.0e5) extreme = 1;
+        out[(int64_t)r * TILE_N] = valid ? v : 0.0;
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&flags[0], 1);
+    if (__any_sync(0xffffffffu, extreme) && lane == 0) atomicOr(&flags[1], 1);
+}
+
+int mbar_b200_create_augmented(mbar_b200_ctx* base, int32_t n_extra, const double* u_extra_host, int64_t ld,
+                               mbar_b200_ctx** out) {
+    MBAR_REQUIRE(base && u_extra_host && out, MBAR_B200_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    MBAR_REQUIRE(base->ready, MBAR_B200_ERR_NOT_READY, "base problem has no u_kn yet");
+    MBAR_REQUIRE(n_extra >= 1 && base->K + n_extra <= 8192, MBAR_B200_ERR_INVALID, "n_extra=%d", n_extra);
+    MBAR_REQUIRE(ld >= base->N, MBAR_B200_ERR_INVALID, "ld=%lld < N_local", (long long)ld);
+    NvtxRange nvtx_("mbar_b200::create_augmented");
+    const int K = base->K, E = n_extra, Kn = K + E;
+    std::vector<double> Nk(base->h_Nk);
+    Nk.resize(Kn, 0.0);
+    mbar_b200_ctx* c = nullptr;
+    MBAR_TRY(mbar_b200_create(&c, base->device, Kn, base->N, Nk.data()));
+    auto fail = [&](int rc) {
+        mbar_b200_destroy(c);
+        return rc;
+    };
+#define AUG_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return fail(MBAR_B200_ERR_CUDA);                                                   \
+        }                                                                                      \
+    } while (0)
+    AUG_CUDA(cudaStreamSynchronize(base->stream));
+    const size_t nPad = (size_t)c->nTiles * TILE_N;
+    AUG_CUDA(cudaMemcpyAsync(c->d_xshift, base->d_xshift, nPad * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    c->sumX = base->sumX;
+    {
+        int64_t grid = (int64_t)c->smCount * 8;
+        if (grid > c->nTiles) grid = c->nTiles;
+        widen_tiles_kernel<<<(unsigned)grid, 256, 0, c->stream>>>(base->d_u, K, Kn, c->nTiles, c->d_u);
+        c->launches++;
+        AUG_CUDA(cudaGetLastError());
+    }
+    // the E new rows: column chunks through a pinned + a device staging block (pageable sources are packed by
+    // the host first, exactly like mbar_b200_upload_u_kn)
+    int64_t cols = (32ll << 20) / (8ll * E);
+    cols = (cols / TILE_N) * TILE_N;
+    if (cols < TILE_N) cols = TILE_N;
+    if (cols > (int64_t)nPad) cols = (int64_t)nPad;
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, u_extra_host) == cudaSuccess)
+        pinned = (attr.type == cudaMemoryTypeHost);
+    else
+        cudaGetLastError();
+    double* d_stage = nullptr;
+    double* h_stage = nullptr;
+    AUG_CUDA(cudaMalloc((void**)&d_stage, (size_t)cols * E * sizeof(double)));
+    if (!pinned) {
+        NumaPrefer numa(c->device);
+        cudaError_t e = cudaHostAlloc((void**)&h_stage, (size_t)cols * E * sizeof(double), cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            cudaFree(d_stage);
+            set_error("cudaHostAlloc failed: %s", cudaGetErrorString(e));
+            return fail(MBAR_B200_ERR_NOMEM);
+        }
+    }
+    int rc = MBAR_B200_OK;
+    for (int64_t n0 = 0; n0 < c->N && rc == MBAR_B200_OK; n0 += cols) {
+        const int64_t w = (c->N - n0 < cols) ? (c->N - n0) : cols;
+        const double* src = u_extra_host + n0;
+        int64_t srcLd = ld;
+        if (!pinned) {
+            cudaStreamSynchronize(c->stream);        // the staging block of the previous chunk has been consumed
+            for (int r = 0; r < E; ++r)
+                std::memcpy(h_stage + (size_t)r * w, u_extra_host + (size_t)r * ld + n0, (size_t)w * sizeof(double));
+            src = h_stage;
+            srcLd = w;
+        }
+        cudaError_t e = cudaMemcpy2DAsync(d_stage, (size_t)cols * sizeof(double), src, (size_t)srcLd * sizeof(double),
+                                          (size_t)w * sizeof(double), E, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) {
+            set_error("append rows: H2D failed: %s", cudaGetErrorString(e));
+            rc = MBAR_B200_ERR_CUDA;
+            break;
+        }
+        c->h2dBytes += (int64_t)w * E * 8;
+        const int64_t nT = (w + TILE_N - 1) / TILE_N;
+        append_rows_kernel<<<(unsigned)nT, 256, 0, c->stream>>>(d_stage, cols, E, K, Kn, n0 / TILE_N, w,
+                                                              c->d_xshift, c->d_u, c->d_flag);
+        c->launches++;
+        if (pinned) cudaStreamSynchronize(c->stream);   // one device staging block: consume before refilling
+    }
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_stage);
+    if (h_stage) cudaFreeHost(h_stage);
+    if (rc != MBAR_B200_OK) return fail(rc);
+    int flags[4] = {0, 0, 0, 0};
+    AUG_CUDA(cudaMemcpy(flags, c->d_flag, sizeof(flags), cudaMemcpyDeviceToHost));
+    AUG_CUDA(cudaMemset(c->d_flag, 0, 4 * sizeof(int)));
+    if (flags[0]) {
+        set_error("appended energies contain NaN");
+        return fail(MBAR_B200_ERR_NAN);
+    }
+    c->unsampledExtreme = base->unsampledExtreme || flags[1] != 0;
+    if (base->d_wgt) {
+        // bootstrap multiplicities travel with the samples
+        AUG_CUDA(cudaMalloc((void**)&c->d_wgt, nPad * sizeof(double)));
+        AUG_CUDA(cudaMalloc((void**)&c->d_sqrtw, nPad * sizeof(double)));
+        AUG_CUDA(cudaMemcpy(c->d_wgt, base->d_wgt, nPad * sizeof(double), cudaMemcpyDeviceToDevice));
+        AUG_CUDA(cudaMemcpy(c->d_sqrtw, base->d_sqrtw, nPad * sizeof(double), cudaMemcpyDeviceToDevice));
+        c->sumW = base->sumW;
+        c->sumXw = base->sumXw;
+    }
+#undef AUG_CUDA
+    c->ready = true;
+    *out = c;
+    return MBAR_B200_OK;
+}
+
 int mbar_b200_upload_u_kn_dev(mbar_b200_ctx* c, const double* u_dev, int64_t ld) {
     MBAR_REQUIRE(c && u_dev, MBAR_B200_ERR_INVALID, "NULL argument");
     MBAR_REQUIRE(ld >= c->N, MBAR_B200_ERR_INVALID, "ld=%lld < N_local", (long long)ld);

@@ -263,13 +263,21 @@ weights_kernel(const double* __restrict__ u, const double* __restrict__ Lp, cons
         const bool valid = tile * TILE_N + lane < N;
         const double* src = u + tile * (int64_t)K * TILE_N;
         double* dst = Wt + tile * (int64_t)K * TILE_N;
-#pragma unroll 4
-        for (int k = warp; k < K; k += 8) {
-            const bool act = (rowmask[k >> 6] >> (k & 63)) & 1ull;
-            const double v = src[k * TILE_N + lane];
-            double wv = 0.0;
-            if (valid && act) wv = sw * exp_fast(fmin(fmax(__ldg(c + k) - v - L, -800.0), 700.0), tab);
-            dst[k * TILE_N + (lane ^ ((k & 7) << 2))] = wv;
+        // 8 rows per thread in flight: the sweep is bound by bytes in flight per SM, not by the exps
+        for (int k0 = warp; k0 < K; k0 += 64) {
+            double v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = (k0 + 8 * i < K) ? src[(k0 + 8 * i) * TILE_N + lane] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = k0 + 8 * i;
+                if (k < K) {
+                    const bool act = (rowmask[k >> 6] >> (k & 63)) & 1ull;
+                    double wv = 0.0;
+                    if (valid && act) wv = sw * exp_fast(fmin(fmax(__ldg(c + k) - v[i] - L, -800.0), 700.0), tab);
+                    dst[k * TILE_N + (lane ^ ((k & 7) << 2))] = wv;
+                }
+            }
         }
     }
 }
@@ -565,9 +573,24 @@ static int ensure_gpart(mbar_b200_ctx* ctx, size_t bytes) {
     return MBAR_B200_OK;
 }
 
+bool ensure_weight_buffer(mbar_b200_ctx* ctx) {
+    static const bool forceOld = std::getenv("MBAR_B200_HESSIAN_INPLACE") != nullptr;
+    if (forceOld) return false;
+    if (ctx->d_Wt) return true;
+    if (ctx->wtAllocFailed) return false;
+    const size_t bytes = (size_t)ctx->nTiles * ctx->K * TILE_N * sizeof(double);
+    if (cudaMalloc((void**)&ctx->d_Wt, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->d_Wt = nullptr;
+        ctx->wtAllocFailed = true;
+        return false;
+    }
+    return true;
+}
+
 // Requires ctx->d_L (shifted-frame L'_n) from the preceding pass at the same f; d_ch = c_k = f_k + log N_k on
 // the device (unsampled rows: f_k when allRows, else ignored).
-int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, LoopState* loop) {
+int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, LoopState* loop, bool weightsReady) {
     const int K = ctx->K;
     MBAR_REQUIRE(ctx->d_L, MBAR_B200_ERR_NOT_READY, "hessian: per-sample L not available");
     const PassLayout lay{K};
@@ -613,15 +636,7 @@ int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, Loo
     const int nPairs = nB * (nB + 1) / 2;
     MBAR_REQUIRE(nPairs < 140, MBAR_B200_ERR_INVALID, "K=%d too large for the Hessian kernel (K <= 2048)", K);
     // weight buffer (8*K*N bytes, kept for the life of the context); without it: round-1 in-place kernel
-    bool materialise = !forceOld;
-    if (materialise && !ctx->d_Wt) {
-        const size_t bytes = (size_t)ctx->nTiles * K * TILE_N * sizeof(double);
-        if (cudaMalloc((void**)&ctx->d_Wt, bytes) != cudaSuccess) {
-            cudaGetLastError();
-            ctx->d_Wt = nullptr;
-            materialise = false;
-        }
-    }
+    const bool materialise = !forceOld && ensure_weight_buffer(ctx);
     // CTAs per pair proportional to its cost per tile: off-diagonal 64 DMMA per k-step on the busiest scheduler,
     // diagonal 36 (materialised) | 4 vs 3 (in-place kernel)
     const double wOff = materialise ? 64.0 : 4.0, wDiag = materialise ? 36.0 : 3.0;
@@ -664,11 +679,15 @@ int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, Loo
     MBAR_TRY(ensure_gpart(ctx, (size_t)nCtas * HB * HB * sizeof(double)));
     static bool attr[16][2] = {{false}};
     if (materialise) {
-        int64_t wgrid = (int64_t)ctx->smCount * 8;
-        if (wgrid > ctx->nTiles) wgrid = ctx->nTiles;
-        weights_kernel<<<(unsigned)wgrid, 256, 0, ctx->stream>>>(ctx->d_u, ctx->d_L, d_ch, mask, K, ctx->N,
-                                                                ctx->nTiles, ctx->d_sqrtw, ctx->d_Wt, loop);
-        MBAR_CUDA(cudaGetLastError());
+        if (!(weightsReady && !allRows)) {
+            // (the fused pass at this f normally wrote the weights already: FusedParams::Wout)
+            int64_t wgrid = (int64_t)ctx->smCount * 8;
+            if (wgrid > ctx->nTiles) wgrid = ctx->nTiles;
+            weights_kernel<<<(unsigned)wgrid, 256, 0, ctx->stream>>>(ctx->d_u, ctx->d_L, d_ch, mask, K, ctx->N,
+                                                                    ctx->nTiles, ctx->d_sqrtw, ctx->d_Wt, loop);
+            MBAR_CUDA(cudaGetLastError());
+            ctx->launches++;
+        }
         MBAR_CUDA(cudaEventRecord(ctx->evH1, ctx->stream));
         const size_t smem = 512 + (size_t)HNS * 2 * HPANEL;
         if (!attr[ctx->device & 15][0]) {
@@ -681,8 +700,9 @@ int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, Loo
                                                                             ctx->d_out + lay.G(), loop);
         MBAR_CUDA(cudaGetLastError());
         snprintf(ctx->lastHessKernel, sizeof(ctx->lastHessKernel),
-                 "weights_kernel + hessian_big_kernel (128x128 block pairs: %d, CTAs %d)", nPairs, nCtas);
-        ctx->launches += 3;
+                 "%s + hessian_big_kernel (128x128 block pairs: %d, CTAs %d)",
+                 (weightsReady && !allRows) ? "weights stored by the fused pass (WST)" : "weights_kernel", nPairs, nCtas);
+        ctx->launches += 2;
     } else {
         MBAR_CUDA(cudaEventRecord(ctx->evH1, ctx->stream));
         const size_t smem = 512 + (size_t)HNS * 2 * HPANEL;
@@ -703,14 +723,14 @@ int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, Loo
     return MBAR_B200_OK;
 }
 
-int launch_hessian(mbar_b200_ctx* ctx, const double* h_f, bool allRows) {
+int launch_hessian(mbar_b200_ctx* ctx, const double* h_f, bool allRows, bool weightsReady) {
     const int K = ctx->K;
     // sampled rows carry N_k W_nk (c = f + log N); with allRows the unsampled rows carry W_nk (c = f)
     for (int k = 0; k < K; ++k)
         ctx->h_f[2 * K + k] = std::isinf(ctx->h_logNk[k]) ? (allRows ? h_f[k] : 0.0) : h_f[k] + ctx->h_logNk[k];
     MBAR_CUDA(cudaMemcpyAsync(ctx->d_c + 2 * K, ctx->h_f + 2 * K, (size_t)K * sizeof(double),
                               cudaMemcpyHostToDevice, ctx->stream));
-    return launch_hessian_dev(ctx, ctx->d_c + 2 * K, allRows, nullptr);
+    return launch_hessian_dev(ctx, ctx->d_c + 2 * K, allRows, nullptr, weightsReady);
 }
 
 }  // namespace mbar

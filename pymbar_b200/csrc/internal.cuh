@@ -157,6 +157,7 @@ struct mbar_b200_ctx {
     int loopBatch = 4;                   // iterations enqueued between two polls of LoopState
     int64_t loopPolls = 0;               // host synchronisations spent polling LoopState
     double* d_Wt = nullptr;              // [nTiles][K][32] materialised N_k W_nk (swizzled) for the Hessian
+    bool wtAllocFailed = false;
     size_t gpartBytes = 0;               // size of d_W (per-CTA partial blocks of the Hessian kernels)
     char lastKernel[200] = "";           // description of the pass-kernel variant launched last
     char lastHessKernel[200] = "";       // ... and of the Hessian kernel path
@@ -182,6 +183,7 @@ struct FusedParams {
     double* out;
     unsigned int* ticket;
     double* Lout;                          // [nTiles*32] shifted-frame L'_n, or NULL
+    double* Wout;                          // [nTiles][K][32] N_k W_nk (swizzled rows) for the Hessian kernels, or NULL
     const double* wgt;                     // [nTiles*32] sample multiplicities or NULL
     double sumW;                           // sum of the multiplicities of this shard (N if unweighted)
     double* f;                             // [K] device f_k (epilogue) or NULL
@@ -233,16 +235,21 @@ int comm_rendezvous(mbar_b200_ctx* ctx);
 int retile_chunk(mbar_b200_ctx* ctx, const double* d_rowmajor, int64_t ldCols, int64_t tile0,
                  int64_t nTilesChunk, int64_t validCols, cudaStream_t s);
 int launch_pass_generic(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool logAll);
-int launch_pass_fused(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, bool* usedOut);
+int launch_pass_fused(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, bool* usedOut,
+                      bool wantW = false, bool* wroteW = nullptr);
 // d_cdst / h_stage: where c = f + log N - mid is staged (default: ctx->d_c / ctx->h_f); midForce: reuse the
 // centring of a previous prepare (candidates evaluated against the same exp(c) range), NaN = derive from f
 int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, FusedParams* out, bool* ok,
-                  double* d_cdst = nullptr, double* h_stage = nullptr);
+                  double* d_cdst = nullptr, double* h_stage = nullptr, bool wantW = false);
 int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p);
 bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, bool allStates, double* midOut, double* spreadOut);
-int launch_hessian(mbar_b200_ctx* ctx, const double* h_f, bool allRows);
+// weightsReady: the fused pass at this f already wrote N_k W_nk into ctx->d_Wt (FusedParams::Wout)
+int launch_hessian(mbar_b200_ctx* ctx, const double* h_f, bool allRows, bool weightsReady = false);
 // same with c_k = f_k + log N_k already on the device (device-resident loops); loop may be NULL
-int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, LoopState* loop);
+int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, LoopState* loop,
+                       bool weightsReady = false);
+// the 8*K*N weight buffer of the K > 64 Hessian path; false when it cannot be allocated (in-place fallback)
+bool ensure_weight_buffer(mbar_b200_ctx* ctx);
 int launch_logw(mbar_b200_ctx* ctx, const double* h_f, double* logW_host, int64_t ld, int expo, int64_t n0,
                 int64_t n);
 int launch_synth(mbar_b200_ctx* ctx, const mbar_b200_synth* spec);

@@ -517,7 +517,7 @@ static int enqueue_adaptive_iteration(mbar_b200_ctx* c, const FusedParams& pF, c
     if (nccl) MBAR_TRY(comm_allreduce(c, c->d_out, K + 2, 0));
     adapt_pre_kernel<<<1, 256, 0, c->stream>>>(c->d_out, c->d_f, c->d_Nk, c->d_rowmask, K, g0, pF.mid, av, c->d_loop);
     // (2) second moments at f (reads L'_n of the pass above)
-    MBAR_TRY(launch_hessian_dev(c, av + AV_CH * K, false, c->d_loop));
+    MBAR_TRY(launch_hessian_dev(c, av + AV_CH * K, false, c->d_loop, pF.Wout != nullptr));
     if (c->nranks > 1) MBAR_TRY(comm_allreduce(c, c->d_out + lay.G(), K * K, 0));
     // (3) Newton candidate: build, factorise, solve; one retry with a relative ridge if not positive definite
     const bool smem = (size_t)n * n * 8 + 2 * ((size_t)n + 2) * 8 <= 200 * 1024;
@@ -578,7 +578,7 @@ int solve_adaptive_device(mbar_b200_ctx* c, double* f, double tol, int32_t maxit
         itersBefore = c->h_loop->iterations;
         FusedParams pF;
         bool ok = false;
-        MBAR_TRY(fused_prepare(c, cur.data(), true, false, &pF, &ok));
+        MBAR_TRY(fused_prepare(c, cur.data(), true, false, &pF, &ok, nullptr, nullptr, true));
         if (!ok) { fallback = true; break; }
         std::memcpy(c->h_f + 4 * K, cur.data(), K * sizeof(double));
         MBAR_CUDA(cudaMemcpyAsync(c->d_f, c->h_f + 4 * K, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -587,6 +587,7 @@ int solve_adaptive_device(mbar_b200_ctx* c, double* f, double tol, int32_t maxit
         pF.first = g0;
         if (c->peerReady) pF.peer = c->peer;
         FusedParams pS = pF, pN = pF;
+        pS.Wout = pN.Wout = nullptr;
         pS.c = c->d_av + AV_CSCI * K;
         pS.out = c->d_outM;
         pS.Lout = nullptr;

@@ -190,7 +190,10 @@ __device__ __forceinline__ void cluster_barrier() {
 // SMs) works on the same tile; CTA `half` (its rank in the cluster) owns states [half*Kh, ...), pulls only
 // those rows from HBM (no redundant traffic) and the per-sample denominators are completed by exchanging
 // the warps' partial sums through distributed shared memory + one cluster barrier per tile.
-template <int R, bool FULL, int CW, int BATCH, int MODE, int CL>
+// WST: the launch also materialises the weights N_k W_nk = e_kn / D_n for the Hessian kernels (tile-major like
+// u_kn, every 256-byte row XOR-swizzled for the DMMA fragment loads): the values sit in registers at that
+// point, so the Newton half of an iteration costs one extra HBM write instead of a separate read+exp+write sweep.
+template <int R, bool FULL, int CW, int BATCH, int MODE, int CL, bool WST = false>
 __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // device-resident loops: a converged (or failed) solver turns the rest of the enqueued batch into no-ops.
@@ -353,9 +356,25 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                 }
                 const bool valid = tile * TILE_N + lane < p.N;
                 if (valid && !(D > 1e-250 && D < 1e250)) bad = 1;
-                const double invD = valid ? (FULL ? 1.0 / D : (1.0 / D) * wn) : 0.0;
+                const double rD = 1.0 / D;
+                const double invD = valid ? (FULL ? rD : rD * wn) : 0.0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) acc[r] = fma(e[r], invD, acc[r]);
+                if (WST) {
+                    // weights of this lane's sample, rows of this warp (bootstrap multiplicities enter the
+                    // second moments as sqrt(w_n) on both factors)
+                    const double inv0 = valid ? ((!FULL && p.wgt) ? rD * sqrt(wn) : rD) : 0.0;
+                    double* wp = p.Wout + ((size_t)tile * K + kbase + k0) * TILE_N;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (FULL || (r < p.Rw && k0 + r < Kl)) {
+                            double wv = e[r] * inv0;
+                            if (MODE & 2) wv *= lds_f64(c_s + k0 + r);
+                            const int k = kbase + k0 + r;
+                            wp[r * TILE_N + (lane ^ ((k & 7) << 2))] = wv;
+                        }
+                    }
+                }
                 if (w == 0 && half == 0) {
                     if (valid) {
                         if (!FULL && p.wgt) {
@@ -571,7 +590,7 @@ bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, bool allState
 
 // Configure the fused kernel for f (host) and stage c = f + log N - mid on the device.
 int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, FusedParams* out,
-                  bool* ok, double* d_cdst, double* h_stage) {
+                  bool* ok, double* d_cdst, double* h_stage, bool wantW) {
     if (!d_cdst) d_cdst = ctx->d_c;
     if (!h_stage) h_stage = ctx->h_f;
     *ok = false;
@@ -635,6 +654,8 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allSta
     if (wantL && !ctx->d_L)
         MBAR_CUDA(cudaMalloc((void**)&ctx->d_L, (size_t)ctx->nTiles * TILE_N * sizeof(double)));
     p.Lout = wantL ? ctx->d_L : nullptr;
+    // weights for the K > 64 Hessian path ride along when the caller is about to evaluate the Hessian at this f
+    p.Wout = (wantW && !allStates && K > 64 && ensure_weight_buffer(ctx)) ? ctx->d_Wt : nullptr;
     p.wgt = ctx->d_wgt;
     p.sumW = ctx->d_wgt ? ctx->sumW : (double)ctx->N;
     for (int k = 0; k < K; ++k)
@@ -664,15 +685,25 @@ int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
         else if (!(p.mode & 2)) { kern = pass_fused_kernel<R_, true, 8, 8, 1, CL_>; which = ID_ + 2; } \
         else { kern = pass_fused_kernel<R_, true, 8, 8, 3, CL_>; which = ID_ + 3; }                    \
     }
+#define PICKW(CL_, ID_)                                                                              \
+    if (Rt == 32 && p.CL == CL_ && p.Wout) {                                                         \
+        if (!full && !(p.mode & 2)) { kern = pass_fused_kernel<32, false, 8, 8, 1, CL_, true>; which = ID_; } \
+        else if (!full) { kern = pass_fused_kernel<32, false, 8, 8, 3, CL_, true>; which = ID_ + 1; }        \
+        else if (!(p.mode & 2)) { kern = pass_fused_kernel<32, true, 8, 8, 1, CL_, true>; which = ID_ + 2; } \
+        else { kern = pass_fused_kernel<32, true, 8, 8, 3, CL_, true>; which = ID_ + 3; }                    \
+    }
     PICK(8, 1, 0) PICK(16, 1, 4) PICK(32, 1, 8) PICK(32, 2, 12) PICK(32, 4, 16) PICK(32, 8, 20)
+    PICKW(1, 24) PICKW(2, 28) PICKW(4, 32) PICKW(8, 36)
+#undef PICKW
 #undef PICK
     MBAR_REQUIRE(kern, MBAR_B200_ERR_INVALID, "no fused kernel variant for K=%d", p.K);
+    MBAR_REQUIRE(!p.Wout || which >= 24, MBAR_B200_ERR_INVALID, "no weight-storing fused variant for K=%d", p.K);
     snprintf(ctx->lastKernel, sizeof(ctx->lastKernel),
-             "pass_fused_kernel<R=%d, %s, CW=8, BATCH=8, MODE=%d (%s), CL=%d> grid=%lld NS=%d TPW=%d", Rt,
+             "pass_fused_kernel<R=%d, %s, CW=8, BATCH=8, MODE=%d (%s), CL=%d%s> grid=%lld NS=%d TPW=%d", Rt,
              full ? "FULL" : "MASKED", (p.mode & 2) ? 3 : 1,
-             (p.mode & 2) ? "LDS table + multiplicative state constant" : "LDS table", p.CL, (long long)grid, p.NS,
-             p.TPW);
-    static size_t attrSetAll[16][24] = {{0}};          // per device: the attribute belongs to the context
+             (p.mode & 2) ? "LDS table + multiplicative state constant" : "LDS table", p.CL,
+             (which >= 24) ? ", WST (weights stored for the Hessian)" : "", (long long)grid, p.NS, p.TPW);
+    static size_t attrSetAll[16][40] = {{0}};          // per device: the attribute belongs to the context
     size_t* attrSet = attrSetAll[ctx->device & 15];
     if (attrSet[which] < smem) {
         MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -703,10 +734,13 @@ int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
     return MBAR_B200_OK;
 }
 
-int launch_pass_fused(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, bool* usedOut) {
+int launch_pass_fused(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, bool* usedOut,
+                      bool wantW, bool* wroteW) {
     FusedParams p;
-    MBAR_TRY(fused_prepare(ctx, h_f, wantL, allStates, &p, usedOut));
+    if (wroteW) *wroteW = false;
+    MBAR_TRY(fused_prepare(ctx, h_f, wantL, allStates, &p, usedOut, nullptr, nullptr, wantW));
     if (!*usedOut) return MBAR_B200_OK;
+    if (wroteW) *wroteW = p.Wout != nullptr;
     return fused_enqueue(ctx, p);
 }
 

@@ -37,17 +37,19 @@ def asymptotic_covariance(G, N_k, method="svd-ew", tol=1.0e-10):
 
 
 def error_of_differences(cov, warning_cutoff=1.0e-10):
-    """mbar.py:1687-1715."""
-    diag = cov.diagonal()
-    d2 = diag + np.vstack(diag) - 2 * cov
-    cutoff = -abs(warning_cutoff)
-    if np.any(d2 < 0.0):
-        if np.any(d2 < cutoff):
-            logger.warning("A squared uncertainty is negative. Largest Magnitude = {0:f}".format(
-                abs(np.min(d2[d2 < cutoff]))))
+    """Standard deviation of every pairwise difference from a covariance matrix (mbar.py:1687-1715):
+    var(x_i - x_j) = C_ii + C_jj - 2 C_ij.  Round-off negatives above -|warning_cutoff| are clipped to zero;
+    anything more negative is reported and left in place (its square root is NaN, as in the reference)."""
+    var = np.diag(cov)
+    spread = np.add.outer(var, var) - 2.0 * np.asarray(cov)
+    negative = spread < 0.0
+    if negative.any():
+        worst = float(spread.min())
+        if worst < -abs(warning_cutoff):
+            logger.warning("A squared uncertainty is negative. Largest Magnitude = {0:f}".format(abs(worst)))
         else:
-            d2[np.logical_and(0 > d2, d2 > cutoff)] = 0.0
-    return np.sqrt(np.array(d2))
+            spread = np.where(negative, 0.0, spread)
+    return np.sqrt(spread)
 
 
 def free_energy_differences(f_k, G, N_k, uncertainty_method=None, warning_cutoff=1.0e-10, return_theta=False):

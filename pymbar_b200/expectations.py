@@ -17,87 +17,87 @@ from __future__ import annotations
 import numpy as np
 
 from . import estimators as est
-from .problem import DeviceProblem
 from .utils import ParameterError
 
 
+def _as_rows(a):
+    a = np.array(a, dtype=np.float64)
+    return a.reshape(1, -1) if a.ndim == 1 else a
+
+
 def expectations_inner(u_kn, N_k, f_k, A_n, u_ln, state_map, uncertainty_method=None, return_theta=False,
-                       device=0):
+                       device=0, problem=None):
     """MBAR.compute_expectations_inner (mbar.py:766-1012) for the analytical (non-bootstrap) methods.
 
-    Parameters follow the reference: A_n [I, N] observables, u_ln [L, N] energies of the states of
-    interest, state_map either a 1-D list of states (free energies only) or [2, S] rows
-    (state index into u_ln, observable index into A_n).  Returns the same dictionary keys:
-    'observables', 'f', 'Theta', 'Amin'."""
-    logfactor = 4.0 * np.finfo(np.float64).eps
-    u_kn = np.asarray(u_kn, dtype=np.float64)
-    N_k = np.asarray(N_k)
+    Same contract as the reference: A_n [I, N] observables, u_ln [L, N] energies of the states of interest,
+    state_map either a 1-D list of states (free energies only) or a [2, S] table whose columns are
+    (row of u_ln, row of A_n).  Returns the keys 'observables', 'f', 'Theta', 'Amin'.
+
+    The appended rows form an augmented problem on top of the RESIDENT u_kn (`DeviceProblem.augmented`): only
+    those rows are uploaded.  `problem` may name the resident DeviceProblem of (u_kn, N_k); otherwise the
+    residency cache of `mbar_solvers` provides it."""
+    from . import mbar_solvers as ms
+
+    u_kn = np.asarray(u_kn)
     f_k = np.asarray(f_k, dtype=np.float64)
-    K, N = u_kn.shape
-    state_map = np.asarray(state_map)
-    if state_map.ndim < 2:
-        state_list = state_map.astype(int).copy()
-        state_map = np.zeros((0, 0), int)
-        S = 0
+    K = u_kn.shape[0]
+    energies = _as_rows(u_ln)
+    obs = _as_rows(A_n)
+    table = np.asarray(state_map)
+    if table.ndim >= 2:
+        of_state, of_obs = table[0].astype(int), table[1].astype(int)
     else:
-        state_map = state_map.astype(int)
-        state_list = state_map[0, :]
-        S = state_map.shape[1]
-    u_ln = np.asarray(u_ln, dtype=np.float64)
-    if u_ln.ndim == 1:
-        u_ln = u_ln.reshape(1, -1)
-    A_n = np.array(A_n, dtype=np.float64)
-    if A_n.ndim == 1:
-        A_n = A_n.reshape(1, -1)
+        of_state, of_obs = table.astype(int), np.zeros(0, dtype=int)
+    n_pairs = len(of_obs)
+    wanted_states = np.unique(of_state)                  # rows of u_ln that become appended states
+    n_states = len(wanted_states)
 
-    L_list = np.unique(state_list)
-    NL = len(L_list)
-    if S > 0:
-        A_list = np.unique(state_map[1, :])
-        A_min = np.zeros(len(A_list))
-    else:
-        A_list = np.zeros(0, dtype=int)
-        A_min = np.zeros(0)
-    logfactors = np.zeros(len(A_list))
-    for i in A_list:
-        A_min[i] = np.min(A_n[i, :])
-        logfactors[i] = np.abs(logfactor * A_min[i])
-        A_n[i, :] = A_n[i, :] - (A_min[i] - logfactors[i])
-
-    # augmented problem: K original states, then the NL states of interest, then the S observables
-    msize = K + NL + S
-    aug = np.empty((msize, N), dtype=np.float64)
-    aug[:K] = u_kn
-    for l in L_list:
-        aug[K + l] = u_ln[l]
+    # observables must be positive to live in the exponent: shift each one used by its minimum (plus a guard
+    # of a few ulp so the smallest value does not become log 0), and give the shift back at the end
+    guard = 4.0 * np.finfo(np.float64).eps
+    floor = {}
+    for i in np.unique(of_obs):
+        lo = obs[i].min()
+        floor[i] = lo - abs(guard * lo)
+    # appended rows: the states of interest, then one row per (state, observable) pair whose "energy" is
+    # u_l - log(A_i - floor_i): its unsampled-state free energy is -log sum_n (A_i - floor_i) e^{-u_l} / D_n
+    extra = np.empty((n_states + n_pairs, u_kn.shape[1]))
+    for pos, l in enumerate(wanted_states):
+        extra[pos] = energies[l]
     with np.errstate(divide="ignore"):
-        for s in range(S):
-            aug[K + NL + s] = u_ln[state_map[0, s]] - np.log(A_n[state_map[1, s]])
-    N_aug = np.zeros(msize)
-    N_aug[:K] = N_k
-    f_aug = np.zeros(msize)
-    f_aug[:K] = f_k
-    result = {}
-    with DeviceProblem(aug, N_aug, device=device) as p:
-        f_new = p.self_consistent_update(f_aug)            # appended rows: -logsumexp_n(-v_an - L_n)
-        f_aug[K:] = f_new[K:]
-        if return_theta:
-            _, G = p.weight_moments(f_aug)
-    # observable estimates: exp(f_l - f_s) + the constant removed for positivity (mbar.py:943-953)
-    if S > 0:
-        A_i = np.exp(f_aug[K + state_map[0, :]] - f_aug[K + NL + np.arange(S)])
-        A_i += A_min[state_map[1, :]] - logfactors[state_map[1, :]]
-        result["observables"] = A_i
-    result["f"] = f_aug[K + state_list]
+        for s in range(n_pairs):
+            extra[n_states + s] = energies[of_state[s]] - np.log(obs[of_obs[s]] - floor[of_obs[s]])
+    row_of_state = {int(l): K + pos for pos, l in enumerate(wanted_states)}
+    rows_l = np.array([row_of_state[int(l)] for l in of_state], dtype=int)
+    rows_s = K + n_states + np.arange(n_pairs)
+
+    f_aug = np.concatenate([f_k, np.zeros(n_states + n_pairs)])
+    N_aug = np.concatenate([np.asarray(N_k, dtype=np.float64), np.zeros(n_states + n_pairs)])
+
+    def run(base):
+        with base.augmented(extra) as q:
+            f_new = q.self_consistent_update(f_aug)        # appended rows: -logsumexp_n(-v_an - L_n)
+            f_aug[K:] = f_new[K:]
+            return q.weight_moments(f_aug)[1] if return_theta else None
+
+    if problem is not None:
+        G = run(problem)
+    else:
+        with ms._borrow(u_kn, N_aug[:K]) as base:
+            G = run(base)
+
+    out = {}
+    if n_pairs:
+        shift = np.array([floor[i] for i in of_obs])
+        out["observables"] = np.exp(f_aug[rows_l] - f_aug[rows_s]) + shift      # mbar.py:943-953
+    out["f"] = f_aug[rows_l]
     if return_theta:
-        Theta_ij = est.asymptotic_covariance(G, N_aug, method=uncertainty_method)
-        si = K + NL + np.arange(S) if S > 0 else np.zeros(0, dtype=int)
-        li = K + state_list
-        idx = np.concatenate((si, li)).astype(int)
-        result["Theta"] = Theta_ij[np.ix_(idx, idx)]
-        if S > 0:
-            result["Amin"] = A_min[state_map[1, np.arange(S)]] - logfactors[state_map[1, np.arange(S)]]
-    return result
+        Theta = est.asymptotic_covariance(G, N_aug, method=uncertainty_method)
+        pick = np.concatenate([rows_s, rows_l]).astype(int)        # observables first, then their states
+        out["Theta"] = Theta[np.ix_(pick, pick)]
+        if n_pairs:
+            out["Amin"] = shift
+    return out
 
 
 def compute_expectations(u_kn, N_k, f_k, A_n, u_ln=None, output="averages", state_dependent=False,

@@ -204,7 +204,12 @@ def mbar_hessian(u_kn, N_k, f_k):
 
 
 def mbar_log_W_nk(u_kn, N_k, f_k):
-    """Eq. 9, [N, K] (mbar_solvers.py:439-473)."""
+    """Eq. 9, [N, K] (mbar_solvers.py:439-473).  While `MBAR.__init__` runs under the installed facade the
+    matrix is not produced yet: the caller receives a ticket that `MBAR.Log_W_nk` redeems on first use."""
+    from . import facade
+
+    if facade.deferring():
+        return facade.LogWeightTicket(u_kn, N_k, f_k)
     u_kn, N_k, f_k = _prep(u_kn, N_k, f_k)
     with _borrow(u_kn, N_k) as p:
         return p.log_W_nk(f_k)

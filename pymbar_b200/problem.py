@@ -107,6 +107,25 @@ class DeviceProblem:
             raise ValueError(f"u_kn must be [{self.K}, {self.N}], got {u.shape}")
         check(self._lib.mbar_b200_upload_u_kn(self._h, C.c_void_p(u.ctypes.data), u.strides[0] // 8))
 
+    def augmented(self, u_extra):
+        """New DeviceProblem = these samples + the rows of `u_extra` [E, N] as unsampled states (the resident
+        tiles are copied on the device, only the new rows are uploaded)."""
+        u = np.asarray(u_extra, dtype=np.float64)
+        if u.ndim == 1:
+            u = u.reshape(1, -1)
+        if u.ndim != 2 or u.shape[1] != self.N:
+            raise ValueError(f"u_extra must be [E, {self.N}], got {u.shape}")
+        if u.strides[1] != 8 or u.strides[0] % 8 or u.strides[0] < 8 * u.shape[1]:
+            u = np.ascontiguousarray(u)
+        h = C.c_void_p()
+        check(self._lib.mbar_b200_create_augmented(self._h, u.shape[0], C.c_void_p(u.ctypes.data),
+                                                   u.strides[0] // 8, C.byref(h)))
+        q = DeviceProblem.__new__(DeviceProblem)
+        q._lib, q._h = self._lib, h
+        q.K, q.N, q.device = self.K + u.shape[0], self.N, self.device
+        q.N_k = np.concatenate([self.N_k, np.zeros(u.shape[0])])
+        return q
+
     def upload_device_ptr(self, ptr, ld):
         check(self._lib.mbar_b200_upload_u_kn_dev(self._h, C.c_void_p(int(ptr)), int(ld)))
 

@@ -31,6 +31,20 @@ class OracleProblem:
     def close(self):
         pass
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        pass
+
+    def weight_moments(self, f):
+        W = orc.mbar_W_nk(self.u, self.N_k, np.asarray(f, float))
+        return W.sum(0), W.T @ W
+
+    def augmented(self, u_extra):
+        u_extra = np.atleast_2d(np.asarray(u_extra, float))
+        return OracleProblem(np.vstack([self.u, u_extra]), np.concatenate([self.N_k, np.zeros(len(u_extra))]))
+
     def _sub(self, f):
         return self.u[self.s], self.N_k[self.s], np.asarray(f, float)[self.s]
 

@@ -28,11 +28,16 @@ def test_reference_acceptance_suite_on_the_gpu_backend(tmp_path):
            "-W", "ignore::pytest.PytestUnknownMarkWarning",
            str(tmp_path / "pymbar" / "tests" / "test_mbar_solvers.py"),
            str(tmp_path / "pymbar" / "tests" / "test_mbar.py")]
-    out = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=3000)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "ref_suite_gpu.log"), "w") as fh:
-        fh.write(out.stdout[-200000:])
-        fh.write("\n--- stderr ---\n" + out.stderr[-20000:])
+    # the reference marks these tests `flaky(max_runs=2..4)` (unseeded samples; the plugin is absent): one rerun
+    for attempt in range(2):
+        out = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=3000)
+        with open(os.path.join(ROOT, "gpurun_out", "ref_suite_gpu.log"), "a" if attempt else "w") as fh:
+            fh.write(f"=== attempt {attempt + 1}: {' '.join(cmd[2:])}\n")
+            fh.write(out.stdout[-200000:])
+            fh.write("\n--- stderr ---\n" + out.stderr[-20000:] + "\n")
+        if out.returncode == 0:
+            break
     lines = [ln for ln in out.stdout.strip().splitlines() if ln.strip()]
     summary = [ln for ln in lines if " passed" in ln or " failed" in ln]
     assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-2000:]

@@ -16,7 +16,12 @@ def test_reference_solver_tests_pass_on_the_mirror(tmp_path):
     env["PYTHONPATH"] = os.pathsep.join([ROOT, os.path.join(ROOT, "oracle", "ref_shim"), "/root/reference"])
     cmd = [sys.executable, "-m", "pytest", "-q", "-p", "tests._mirror_plugin", "-p", "no:cacheprovider",
            "/root/reference/pymbar/tests/test_mbar_solvers.py", "/root/reference/pymbar/tests/test_mbar.py"]
-    out = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=1500)
+    env["PYMBAR_DISABLE_JAX"] = "1"
+    # the reference marks these tests `flaky(max_runs=2..4)` (unseeded samples, plugin absent here): same allowance
+    for _attempt in range(2):
+        out = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=1500)
+        if out.returncode == 0:
+            break
     tail = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-500:]
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert " passed" in tail and " failed" not in tail and " error" not in tail, tail

@@ -11,6 +11,10 @@ p.synthesize(np.linspace(1, 5, K), np.linspace(1, 3, K), seed=0)
 f = np.zeros(K)
 if what == "hessian":
     p.hessian(f); p.hessian(f)
+    print(p.last_kernels(), p.last_hessian_ms())
+elif what == "moments":       # all-state second moments: the weights_kernel path
+    p.weight_moments(f)
+    print(p.last_kernels(), p.last_hessian_ms())
 else:
     p.set_kernel(what)
     for _ in range(3):
