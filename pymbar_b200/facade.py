@@ -28,6 +28,7 @@ from . import estimators as est
 
 _TLS = threading.local()
 _SAVED = {}
+STATS = {"tickets": 0, "redeemed": 0, "moments": 0, "expectations": 0}
 
 
 class LogWeightTicket:
@@ -37,10 +38,12 @@ class LogWeightTicket:
 
     def __init__(self, u_kn, N_k, f_k):
         self.u_kn, self.N_k, self.f_k = u_kn, np.array(N_k), np.array(f_k, dtype=np.float64)
+        STATS["tickets"] += 1
 
     def redeem(self):
         from . import mbar_solvers as ms
 
+        STATS["redeemed"] += 1
         return ms.mbar_log_W_nk(self.u_kn, self.N_k, self.f_k)
 
 
@@ -55,6 +58,7 @@ def _moments(mbar):
         return cached[0], cached[1]
     from . import mbar_solvers as ms
 
+    STATS["moments"] += 1
     with ms._borrow(mbar.u_kn, np.asarray(mbar.N_k, dtype=np.float64)) as p:
         S, G = p.weight_moments(np.asarray(mbar.f_k, dtype=np.float64))
     mbar.__dict__["_b200_moments"] = (S, G, np.array(mbar.f_k))
@@ -146,6 +150,7 @@ def install_on(MBAR):
         from . import expectations as ex
         from . import mbar_solvers as ms
 
+        STATS["expectations"] += 1
         return ex.expectations_inner(self.u_kn, self.N_k, self.f_k, A_n, u_ln, state_map,
                                      uncertainty_method=uncertainty_method, return_theta=return_theta,
                                      device=ms._DEVICE)

@@ -40,6 +40,10 @@ def pytest_terminal_summary(terminalreporter):
     import pymbar_b200
 
     loaded = [ln.split()[-1] for ln in open("/proc/self/maps") if "libmbar_b200.so" in ln]
+    from pymbar_b200 import facade
+
+    terminalreporter.write_line(f"pymbar_b200 facade: {facade.STATS} (Log_W_nk tickets issued inside MBAR.__init__ / "
+                                "downloaded on first read; estimators and expectations served from device moments)")
     terminalreporter.write_line(
         f"pymbar_b200 backend: solve_mbar_for_all_states calls={CALLS['solve']} mbar_log_W_nk calls={CALLS['logW']} "
         f"native library mapped={sorted(set(loaded))}")
