@@ -15,6 +15,9 @@ the CPU.  With the facade installed:
   compute_multiple_expectations, compute_perturbed_free_energies and compute_entropy_and_enthalpy — is
   answered by the augmented-problem formulation of `pymbar_b200.expectations`.
 
+* `_initialize_with_bar` (:1936-1988, `MBAR(initialize="BAR")`) uses `pymbar_b200.initialize` (samples grouped by
+  state once, Brent on Bennett's equation).
+
 Anything outside what the device path implements (bootstrap uncertainties, `uncertainty_method="svd"`) calls
 the original method, which then reads `self.Log_W_nk` and materialises it.  `uninstall()` restores the class.
 """
@@ -81,7 +84,7 @@ def install_on(MBAR):
         return
     saved = {name: MBAR.__dict__.get(name) for name in
              ("__init__", "Log_W_nk", "compute_effective_sample_number", "compute_overlap",
-              "compute_free_energy_differences", "compute_expectations_inner")}
+              "compute_free_energy_differences", "compute_expectations_inner", "_initialize_with_bar")}
     _SAVED[MBAR] = saved
     orig_init = saved["__init__"]
     orig_fed = saved["compute_free_energy_differences"]
@@ -155,6 +158,12 @@ def install_on(MBAR):
                                      uncertainty_method=uncertainty_method, return_theta=return_theta,
                                      device=ms._DEVICE)
 
+    def _initialize_with_bar(self, u_kn, f_k_init=None):
+        from . import initialize as init
+
+        return init.initialize_with_bar(u_kn, self.N_k, self.x_kindices, f_k_init)
+
+    MBAR._initialize_with_bar = _initialize_with_bar
     MBAR.__init__ = __init__
     MBAR.Log_W_nk = property(_get_logw, _set_logw, doc="log weights [N, K] (mbar.py:455), downloaded on first use")
     MBAR.compute_effective_sample_number = compute_effective_sample_number

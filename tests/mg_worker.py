@@ -79,6 +79,31 @@ def main():
         worst = max(worst, max(errs.values()))
         assert not bad, (name, rank, bad)
         p.close()
+    # the mirror's sharded entry points (pymbar_b200.sharded): reference signatures, this rank's columns only
+    from pymbar_b200 import mbar_solvers as ms
+    from pymbar_b200 import sharded as sh
+
+    for name in ("small_empty_state", "osc_50x100"):
+        z = _cases.load(name)
+        u, N_k = z["u_kn"], z["N_k"]
+        Ntot = u.shape[1]
+        lo, hi = Ntot * rank // world, Ntot * (rank + 1) // world
+        sws = np.where(N_k != 0)[0]
+        for proto_name, proto in (("default", ms.DEFAULT_SOLVER_PROTOCOL), ("robust", ms.ROBUST_SOLVER_PROTOCOL)):
+            proto = tuple({k: (dict(v) if isinstance(v, dict) else v) for k, v in st.items()} for st in proto)
+            f = sh.solve_mbar_for_all_states(np.ascontiguousarray(u[:, lo:hi]), N_k, np.zeros(len(N_k)), sws, proto)
+            err = np.max(np.abs(f - z[f"fk_{proto_name}"]))
+            assert err < 1e-8, (name, proto_name, err)
+            worst = max(worst, err)
+            gb = [None] * world
+            dist.all_gather_object(gb, f.tobytes())
+            assert all(b == gb[0] for b in gb), "sharded solve: ranks disagree"
+        lw = sh.mbar_log_W_nk(np.ascontiguousarray(u[:, lo:hi]), N_k, z["fk_default"])
+        ref_lw = orc.mbar_log_W_nk(u, N_k.astype(float), z["fk_default"])[lo:hi]
+        assert np.max(np.abs(lw - ref_lw)) < 1e-9
+        S, G = sh.weight_moments(np.ascontiguousarray(u[:, lo:hi]), N_k, z["fk_default"])
+        W = orc.mbar_W_nk(u, N_k.astype(float), z["fk_default"])
+        assert np.max(np.abs(G - W.T @ W)) < 1e-9 * np.max(W.T @ W) + 1e-14
     dist.barrier()
     if rank == 0:
         print(f"MG_OK world={world} worst_err={worst:.3e} (primitives, NCCL + in-kernel peer exchange, "

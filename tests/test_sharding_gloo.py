@@ -74,3 +74,31 @@ def test_bench_rank_helpers():
     assert N_k.sum() == 100 and np.all(N_k[:-1] == 14)
     O, k = bench.workload_params(256)
     assert O[0] == 1 and O[-1] == 5 and k[0] == 1 and k[-1] == 3
+
+
+def _exchange_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pymbar_b200.sharded import Exchange
+
+    ex = Exchange()
+    got = ex.broadcast(b"id-from-rank-0" if rank == 0 else None)
+    gathered = ex.all_gather(bytes([rank]) * 4)
+    q.put((rank, got == b"id-from-rank-0" and gathered == [bytes([r]) * 4 for r in range(world)]
+           and ex.rank == rank and ex.world == world))
+    dist.destroy_process_group()
+
+
+def test_rendezvous_transport_of_the_sharded_entry_points():
+    """pymbar_b200.sharded.Exchange (what carries the NCCL id and the cudaIpc handles) under a 2-rank gloo group"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
