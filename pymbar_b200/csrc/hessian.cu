@@ -58,7 +58,8 @@ __device__ __forceinline__ void convert_row(double* P, int row, int lane, double
 // pairs only multiply the 10 lower-triangular 32 x 32 sub-blocks (3 instead of 4 per scheduler), so
 // they get 3/4 of the CTAs an off-diagonal pair gets.
 struct HessSplit {
-    int nPairs;
+    int nPairs;        // pairs handled by THIS launch
+    int pairBase;      // global index of its first pair (K > 2048 needs several launches)
     int pairStart[140];
 };
 
@@ -78,7 +79,7 @@ hessian_inplace_kernel(const double* __restrict__ u, const double* __restrict__ 
     while (pair + 1 < split.nPairs && (int)blockIdx.x >= split.pairStart[pair + 1]) ++pair;
     const int chunk = blockIdx.x - split.pairStart[pair];
     const int nChunks = split.pairStart[pair + 1] - split.pairStart[pair];
-    int bi = 0, rem = pair;                       // pairs enumerated (0,0),(1,0),(1,1),(2,0),...
+    int bi = 0, rem = pair + split.pairBase;      // pairs enumerated (0,0),(1,0),(1,1),(2,0),...
     while (rem > bi) { rem -= bi + 1; ++bi; }
     const int bj = rem;
     const bool diag = (bi == bj);
@@ -226,7 +227,7 @@ hessian_inplace_kernel(const double* __restrict__ u, const double* __restrict__ 
 __global__ void __launch_bounds__(256)
 hessian_reduce_kernel(const double* __restrict__ Gpart, int K, const HessSplit split, double* __restrict__ G) {
     const int pair = blockIdx.x;
-    int bi = 0, rem = pair;
+    int bi = 0, rem = pair + split.pairBase;
     while (rem > bi) { rem -= bi + 1; ++bi; }
     const int bj = rem;
     const int c0 = split.pairStart[pair], c1 = split.pairStart[pair + 1];
@@ -301,7 +302,7 @@ hessian_big_kernel(const double* __restrict__ Wt, int K, int64_t nTiles, const H
     while (pair + 1 < split.nPairs && (int)blockIdx.x >= split.pairStart[pair + 1]) ++pair;
     const int chunk = blockIdx.x - split.pairStart[pair];
     const int nChunks = split.pairStart[pair + 1] - split.pairStart[pair];
-    int bi = 0, rem = pair;                       // pairs enumerated (0,0),(1,0),(1,1),(2,0),...
+    int bi = 0, rem = pair + split.pairBase;      // pairs enumerated (0,0),(1,0),(1,1),(2,0),...
     while (rem > bi) { rem -= bi + 1; ++bi; }
     const int bj = rem;
     const bool diag = (bi == bj);
@@ -412,7 +413,7 @@ hessian_big_reduce_kernel(const double* __restrict__ Gpart, int K, const HessSpl
                           const LoopState* loop) {
     if (loop && *reinterpret_cast<const volatile int*>(&loop->done)) return;
     const int pair = blockIdx.x;
-    int bi = 0, rem = pair;
+    int bi = 0, rem = pair + split.pairBase;
     while (rem > bi) { rem -= bi + 1; ++bi; }
     const int bj = rem;
     const int c0 = split.pairStart[pair], c1 = split.pairStart[pair + 1];
@@ -633,32 +634,55 @@ int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, Loo
     }
 
     const int nB = (K + HB - 1) / HB;
-    const int nPairs = nB * (nB + 1) / 2;
-    MBAR_REQUIRE(nPairs < 140, MBAR_B200_ERR_INVALID, "K=%d too large for the Hessian kernel (K <= 2048)", K);
+    const int nPairsAll = nB * (nB + 1) / 2;
     // weight buffer (8*K*N bytes, kept for the life of the context); without it: round-1 in-place kernel
     const bool materialise = !forceOld && ensure_weight_buffer(ctx);
     // CTAs per pair proportional to its cost per tile: off-diagonal 64 DMMA per k-step on the busiest scheduler,
     // diagonal 36 (materialised) | 4 vs 3 (in-place kernel)
     const double wOff = materialise ? 64.0 : 4.0, wDiag = materialise ? 36.0 : 3.0;
-    HessSplit split{};
-    split.nPairs = nPairs;
-    {
+    static bool attr[16][2] = {{false}};
+    const size_t smem = 512 + (size_t)HNS * 2 * HPANEL;
+    if (materialise && !(weightsReady && !allRows)) {
+        // (the fused pass at this f normally wrote the weights already: FusedParams::Wout)
+        int64_t wgrid = (int64_t)ctx->smCount * 8;
+        if (wgrid > ctx->nTiles) wgrid = ctx->nTiles;
+        weights_kernel<<<(unsigned)wgrid, 256, 0, ctx->stream>>>(ctx->d_u, ctx->d_L, d_ch, mask, K, ctx->N,
+                                                                ctx->nTiles, ctx->d_sqrtw, ctx->d_Wt, loop);
+        MBAR_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+    MBAR_CUDA(cudaEventRecord(ctx->evH1, ctx->stream));
+    // pairs in launches of at most 128 (K <= 2048: one launch; the split table is a kernel parameter)
+    int totalCtas = 0;
+    for (int base = 0; base < nPairsAll; base += 128) {
+        const int nPairs = std::min(128, nPairsAll - base);
+        HessSplit split{};
+        split.nPairs = nPairs;
+        split.pairBase = base;
+        std::vector<char> isDiag(nPairs);
+        {
+            int bi = 0, rem = base;
+            while (rem > bi) { rem -= bi + 1; ++bi; }
+            int bj = rem;
+            for (int p = 0; p < nPairs; ++p) {
+                isDiag[p] = (bi == bj);
+                if (++bj > bi) { ++bi; bj = 0; }
+            }
+        }
         double wsum = 0.0;
-        for (int bi = 0; bi < nB; ++bi)
-            for (int bj = 0; bj <= bi; ++bj) wsum += (bi == bj) ? wDiag : wOff;
-        int total = ctx->smCount > nPairs ? ctx->smCount : nPairs;
+        for (int p = 0; p < nPairs; ++p) wsum += isDiag[p] ? wDiag : wOff;
+        const int total = ctx->smCount > nPairs ? ctx->smCount : nPairs;
         // largest-remainder apportionment of `total` CTAs (every SM gets exactly one CTA when it fits)
         int used = 0;
         std::vector<int> cnt(nPairs);
         std::vector<double> frac(nPairs);
-        for (int bi = 0, p = 0; bi < nB; ++bi)
-            for (int bj = 0; bj <= bi; ++bj, ++p) {
-                const double x = total * ((bi == bj) ? wDiag : wOff) / wsum;
-                cnt[p] = (int)x;
-                if (cnt[p] < 1) cnt[p] = 1;
-                frac[p] = x - (int)x;
-                used += cnt[p];
-            }
+        for (int p = 0; p < nPairs; ++p) {
+            const double x = total * (isDiag[p] ? wDiag : wOff) / wsum;
+            cnt[p] = (int)x;
+            if (cnt[p] < 1) cnt[p] = 1;
+            frac[p] = x - (int)x;
+            used += cnt[p];
+        }
         while (used < total) {
             int best = 0;
             for (int p = 1; p < nPairs; ++p)
@@ -674,50 +698,39 @@ int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, Loo
             used += cnt[p];
         }
         split.pairStart[nPairs] = used;
-    }
-    const int nCtas = split.pairStart[nPairs];
-    MBAR_TRY(ensure_gpart(ctx, (size_t)nCtas * HB * HB * sizeof(double)));
-    static bool attr[16][2] = {{false}};
-    if (materialise) {
-        if (!(weightsReady && !allRows)) {
-            // (the fused pass at this f normally wrote the weights already: FusedParams::Wout)
-            int64_t wgrid = (int64_t)ctx->smCount * 8;
-            if (wgrid > ctx->nTiles) wgrid = ctx->nTiles;
-            weights_kernel<<<(unsigned)wgrid, 256, 0, ctx->stream>>>(ctx->d_u, ctx->d_L, d_ch, mask, K, ctx->N,
-                                                                    ctx->nTiles, ctx->d_sqrtw, ctx->d_Wt, loop);
+        const int nCtas = used;
+        totalCtas += nCtas;
+        MBAR_TRY(ensure_gpart(ctx, (size_t)nCtas * HB * HB * sizeof(double)));
+        if (materialise) {
+            if (!attr[ctx->device & 15][0]) {
+                MBAR_CUDA(cudaFuncSetAttribute(hessian_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr[ctx->device & 15][0] = true;
+            }
+            hessian_big_kernel<<<nCtas, 512, smem, ctx->stream>>>(ctx->d_Wt, K, ctx->nTiles, split, ctx->d_W, loop);
             MBAR_CUDA(cudaGetLastError());
-            ctx->launches++;
+            hessian_big_reduce_kernel<<<dim3(nPairs, 16), 256, 0, ctx->stream>>>(ctx->d_W, K, split,
+                                                                                ctx->d_out + lay.G(), loop);
+            MBAR_CUDA(cudaGetLastError());
+        } else {
+            if (!attr[ctx->device & 15][1]) {
+                MBAR_CUDA(cudaFuncSetAttribute(hessian_inplace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr[ctx->device & 15][1] = true;
+            }
+            hessian_inplace_kernel<<<nCtas, 512, smem, ctx->stream>>>(ctx->d_u, ctx->d_L, d_ch, mask, K, ctx->N,
+                                                                     ctx->nTiles, split, ctx->d_W, ctx->d_sqrtw);
+            MBAR_CUDA(cudaGetLastError());
+            hessian_reduce_kernel<<<dim3(nPairs, 16), 256, 0, ctx->stream>>>(ctx->d_W, K, split, ctx->d_out + lay.G());
+            MBAR_CUDA(cudaGetLastError());
         }
-        MBAR_CUDA(cudaEventRecord(ctx->evH1, ctx->stream));
-        const size_t smem = 512 + (size_t)HNS * 2 * HPANEL;
-        if (!attr[ctx->device & 15][0]) {
-            MBAR_CUDA(cudaFuncSetAttribute(hessian_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr[ctx->device & 15][0] = true;
-        }
-        hessian_big_kernel<<<nCtas, 512, smem, ctx->stream>>>(ctx->d_Wt, K, ctx->nTiles, split, ctx->d_W, loop);
-        MBAR_CUDA(cudaGetLastError());
-        hessian_big_reduce_kernel<<<dim3(nPairs, 16), 256, 0, ctx->stream>>>(ctx->d_W, K, split,
-                                                                            ctx->d_out + lay.G(), loop);
-        MBAR_CUDA(cudaGetLastError());
+        ctx->launches += 2;
+    }
+    if (materialise)
         snprintf(ctx->lastHessKernel, sizeof(ctx->lastHessKernel),
                  "%s + hessian_big_kernel (128x128 block pairs: %d, CTAs %d)",
-                 (weightsReady && !allRows) ? "weights stored by the fused pass (WST)" : "weights_kernel", nPairs, nCtas);
-        ctx->launches += 2;
-    } else {
-        MBAR_CUDA(cudaEventRecord(ctx->evH1, ctx->stream));
-        const size_t smem = 512 + (size_t)HNS * 2 * HPANEL;
-        if (!attr[ctx->device & 15][1]) {
-            MBAR_CUDA(cudaFuncSetAttribute(hessian_inplace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr[ctx->device & 15][1] = true;
-        }
-        hessian_inplace_kernel<<<nCtas, 512, smem, ctx->stream>>>(ctx->d_u, ctx->d_L, d_ch, mask, K, ctx->N,
-                                                                 ctx->nTiles, split, ctx->d_W, ctx->d_sqrtw);
-        MBAR_CUDA(cudaGetLastError());
-        hessian_reduce_kernel<<<dim3(nPairs, 16), 256, 0, ctx->stream>>>(ctx->d_W, K, split, ctx->d_out + lay.G());
-        MBAR_CUDA(cudaGetLastError());
-        snprintf(ctx->lastHessKernel, sizeof(ctx->lastHessKernel), "hessian_inplace_kernel (round 1), CTAs %d", nCtas);
-        ctx->launches += 2;
-    }
+                 (weightsReady && !allRows) ? "weights stored by the fused pass (WST)" : "weights_kernel", nPairsAll,
+                 totalCtas);
+    else
+        snprintf(ctx->lastHessKernel, sizeof(ctx->lastHessKernel), "hessian_inplace_kernel (round 1), CTAs %d", totalCtas);
     MBAR_CUDA(cudaEventRecord(ctx->evH2, ctx->stream));
     ctx->passes++;
     return MBAR_B200_OK;

@@ -224,3 +224,14 @@ def test_scipy_methods_against_the_device(lib, method):
     assert np.max(np.abs(f - f_ref)) < (1e-6 if method == "CG" else 1e-7)
     assert np.max(np.abs(f - z["fk_default"])) < 1e-6
     ms.clear_cache()
+
+
+def test_hessian_beyond_2048_states(lib):
+    """K > 2048: generic pass + the block-pair Hessian in several launches (153 pairs at K = 2100); ADVICE r1:
+    mbar_hessian must not refuse what mbar_b200_create accepts."""
+    K = 2100
+    u, N_k, f = _random_problem(K, 2 * K, seed=77)
+    with lib.DeviceProblem(u, N_k) as p:
+        H = p.hessian(f)
+        H_ref = orc.mbar_hessian(u, N_k, f)
+        np.testing.assert_allclose(H, H_ref, rtol=1e-9, atol=1e-11 * np.max(np.abs(H_ref)))
