@@ -798,6 +798,7 @@ int mbar_b200_sci_iterate(mbar_b200_ctx* c, double* f, int32_t iters) {
     if (cudaEventElapsedTime(&ms, c->evA, c->evB) == cudaSuccess) c->lastPassMs = ms;
     MBAR_REQUIRE(!(iters > 0 && c->h_out[lay.flag()] >= 1.0e6), MBAR_B200_ERR_COMM,
                  "peer exchange timed out inside the pass kernel (a rank did not arrive)");
+    if (p.debugSkip) return MBAR_B200_OK;   // memory-pipeline probe: the arithmetic was skipped, nothing to return
     if (iters > 0 && c->h_out[lay.flag()] != 0.0) c->h_f[4 * K + c->firstActive] = NAN;  // force the robust redo
     bool finite = true;
     for (int k : c->active) finite = finite && std::isfinite(c->h_f[4 * K + k]);
