@@ -298,7 +298,24 @@ int mbar_b200_pass_multi(mbar_b200_ctx* c, int32_t M, const double* f, double* S
     MBAR_TRY(rc0);
     bool fast = c->kernelChoice != MBAR_B200_KERNEL_GENERIC;
     FusedParams p[2];
-    for (int m = 0; m < M && fast; ++m) {
+    bool batched = false;
+    static const bool noM2 = std::getenv("MBAR_B200_NO_M2") != nullptr;
+    if (fast && M == 2 && !noM2) {
+        // one launch for both candidates (pass_fused_kernel<..., M = 2>): one read of u_kn, one exp per entry
+        bool ok0 = false, ok1 = false;
+        MBAR_TRY(fused_prepare(c, f, false, false, &p[0], &ok0, c->d_c, c->h_f, false, 2));
+        if (ok0)
+            MBAR_TRY(fused_prepare(c, f + K, false, false, &p[1], &ok1, c->d_av + 4 * (size_t)K, c->h_f + 6 * (size_t)K,
+                                   false, 2));
+        if (ok0 && ok1) {
+            p[0].c2 = p[1].c;
+            p[0].mid2 = p[1].mid;
+            p[0].out = c->d_outM;
+            p[0].out2 = c->d_outM + lay.size(false);
+            batched = true;
+        }
+    }
+    for (int m = 0; m < M && fast && !batched; ++m) {
         bool ok = false;
         // candidate m stages its constants in its own device row / pinned row (the copies are asynchronous)
         MBAR_TRY(fused_prepare(c, f + (size_t)m * K, false, false, &p[m], &ok,
@@ -307,9 +324,15 @@ int mbar_b200_pass_multi(mbar_b200_ctx* c, int32_t M, const double* f, double* S
         fast = ok;
     }
     if (fast) {
-        for (int m = 0; m < M; ++m) {
-            MBAR_TRY(fused_enqueue(c, p[m]));
-            MBAR_TRY(comm_allreduce(c, p[m].out, K + 2, 0));
+        if (batched) {
+            MBAR_TRY(fused_enqueue(c, p[0]));
+            MBAR_TRY(comm_allreduce(c, p[0].out, K + 2, 0));
+            MBAR_TRY(comm_allreduce(c, p[0].out2, K + 2, 0));
+        } else {
+            for (int m = 0; m < M; ++m) {
+                MBAR_TRY(fused_enqueue(c, p[m]));
+                MBAR_TRY(comm_allreduce(c, p[m].out, K + 2, 0));
+            }
         }
         MBAR_CUDA(cudaMemcpyAsync(c->h_out, c->d_outM, (size_t)M * lay.size(false) * sizeof(double),
                                   cudaMemcpyDeviceToHost, c->stream));
@@ -876,7 +899,7 @@ int mbar_b200_comm_init(mbar_b200_ctx* c, int32_t nranks, int32_t rank, const vo
     return MBAR_B200_OK;
 }
 
-static size_t inbox_doubles(int K) { return (size_t)2 * MAX_PEERS * (K + 2); }
+static size_t inbox_doubles(int K) { return (size_t)2 * MAX_PEERS * 2 * (K + 2); }   // (2 candidates per launch)
 
 int mbar_b200_peer_export(mbar_b200_ctx* c, void* handle_out) {
     MBAR_REQUIRE(c && handle_out, MBAR_B200_ERR_INVALID, "NULL argument");

@@ -177,6 +177,10 @@ namespace mbar {
 struct FusedParams {
     const double* u;
     const double* c;                       // [K] f_k + log N_k - mid (sampled rows)
+    const double* c2;                      // second candidate (M == 2): [K] f2_k + log N_k - mid2
+    double* out2;                          // ... and its packed result
+    double mid2;
+    int M;                                 // candidates evaluated per launch (1 or 2)
     const unsigned long long* rowmask;
     const double* Nk;
     double* partial;                       // [grid][K + 2]
@@ -240,7 +244,7 @@ int launch_pass_fused(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool al
 // d_cdst / h_stage: where c = f + log N - mid is staged (default: ctx->d_c / ctx->h_f); midForce: reuse the
 // centring of a previous prepare (candidates evaluated against the same exp(c) range), NaN = derive from f
 int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, FusedParams* out, bool* ok,
-                  double* d_cdst = nullptr, double* h_stage = nullptr, bool wantW = false);
+                  double* d_cdst = nullptr, double* h_stage = nullptr, bool wantW = false, int M = 1);
 int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p);
 bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, bool allStates, double* midOut, double* spreadOut);
 // weightsReady: the fused pass at this f already wrote N_k W_nk into ctx->d_Wt (FusedParams::Wout)

@@ -504,7 +504,7 @@ int solve_sci_device(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter, m
 
 // One adaptive iteration, enqueued with no host synchronisation.
 static int enqueue_adaptive_iteration(mbar_b200_ctx* c, const FusedParams& pF, const FusedParams& pS,
-                                      const FusedParams& pN) {
+                                      const FusedParams& pN, const FusedParams* pM) {
     const int K = c->K;
     const PassLayout lay{K};
     const int na = (int)c->active.size();
@@ -538,11 +538,20 @@ static int enqueue_adaptive_iteration(mbar_b200_ctx* c, const FusedParams& pF, c
                                                  attempt == 1, c->d_loop);
     }
     MBAR_CUDA(cudaGetLastError());
-    // (4) both candidates
-    MBAR_TRY(fused_enqueue(c, pS));
-    if (nccl) MBAR_TRY(comm_allreduce(c, pS.out, K + 2, 0));
-    MBAR_TRY(fused_enqueue(c, pN));
-    if (nccl) MBAR_TRY(comm_allreduce(c, pN.out, K + 2, 0));
+    // (4) both candidates: ONE launch evaluates f_sci and f_nr on the same staged tiles (M = 2) when the kernel
+    //     family allows it, otherwise two launches
+    if (pM) {
+        MBAR_TRY(fused_enqueue(c, *pM));
+        if (nccl) {
+            MBAR_TRY(comm_allreduce(c, pM->out, K + 2, 0));
+            MBAR_TRY(comm_allreduce(c, pM->out2, K + 2, 0));
+        }
+    } else {
+        MBAR_TRY(fused_enqueue(c, pS));
+        if (nccl) MBAR_TRY(comm_allreduce(c, pS.out, K + 2, 0));
+        MBAR_TRY(fused_enqueue(c, pN));
+        if (nccl) MBAR_TRY(comm_allreduce(c, pN.out, K + 2, 0));
+    }
     // (5) choice + convergence + next iteration's vectors
     adapt_post_kernel<<<1, 256, 0, c->stream>>>(pS.out, pN.out, av, c->d_f, c->d_c, c->d_Nk, c->d_rowmask, K, g0,
                                                pF.mid, c->d_loop);
@@ -570,7 +579,7 @@ int solve_adaptive_device(mbar_b200_ctx* c, double* f, double tol, int32_t maxit
     MBAR_CUDA(cudaEventRecord(e0, c->stream));
     MBAR_TRY(loop_begin(c, tol, maxiter, min_sc_iter, gamma));
     if (c->peerReady) MBAR_TRY(comm_rendezvous(c));
-    bool fallback = false;
+    bool fallback = false, usedM2 = false;
     int itersBefore = 0;
     int rc = MBAR_B200_OK;
     for (;;) {
@@ -594,7 +603,26 @@ int solve_adaptive_device(mbar_b200_ctx* c, double* f, double tol, int32_t maxit
         pN.c = c->d_av + AV_CNR * K;
         pN.out = c->d_outM + PassLayout{K}.size(false);
         pN.Lout = nullptr;
-        for (int b = 0; b < c->loopBatch; ++b) MBAR_TRY(enqueue_adaptive_iteration(c, pF, pS, pN));
+        // candidate-batched pass (same f -> same centring `mid` as pF; the device kernels write its constants)
+        FusedParams pM;
+        bool okM = false;
+        static const bool noM2 = std::getenv("MBAR_B200_NO_M2") != nullptr;
+        if (!noM2)
+            MBAR_TRY(fused_prepare(c, cur.data(), false, false, &pM, &okM, c->d_av + AV_CSCI * K, c->h_f + 6 * K,
+                                   false, 2));
+        if (okM) {
+            pM.loop = c->d_loop;
+            pM.first = g0;
+            if (c->peerReady) pM.peer = c->peer;
+            pM.c = c->d_av + AV_CSCI * K;
+            pM.c2 = c->d_av + AV_CNR * K;
+            pM.mid2 = pM.mid;
+            pM.out = pS.out;
+            pM.out2 = pN.out;
+        }
+        for (int b = 0; b < c->loopBatch; ++b)
+            MBAR_TRY(enqueue_adaptive_iteration(c, pF, pS, pN, okM ? &pM : nullptr));
+        usedM2 = usedM2 || okM;
         MBAR_TRY(loop_poll(c));
         const LoopState& st = *c->h_loop;
         if (st.status != 0) {
@@ -610,7 +638,7 @@ int solve_adaptive_device(mbar_b200_ctx* c, double* f, double tol, int32_t maxit
     r.iterations = st.iterations;
     r.nr_iterations = st.nr_iterations;
     r.sci_iterations = st.sci_iterations;
-    r.passes = 3 * st.iterations;
+    r.passes = (usedM2 ? 2 : 3) * st.iterations;
     r.hessian_passes = st.iterations;
     r.success = st.success;
     r.max_delta = st.max_delta;
@@ -622,7 +650,7 @@ int solve_adaptive_device(mbar_b200_ctx* c, double* f, double tol, int32_t maxit
         rc = solve_adaptive_stepped(c, snap.data(), tol, left, msi, gamma, &r2);
         cur = snap;
         r2.iterations += itersBefore;
-        r2.passes += 3 * itersBefore;
+        r2.passes += (usedM2 ? 2 : 3) * itersBefore;
         r2.hessian_passes += itersBefore;
         r = r2;
     }

@@ -38,10 +38,12 @@ namespace mbar {
 __host__ __device__ constexpr int fused_slots(int CL) { return CL > 1 ? CL * 8 : 16; }
 constexpr uint32_t FUSED_COPY_CHUNK = 32768;
 
-__host__ __device__ inline size_t fused_smem_header(int K, int CL) {
-    // tab[32] | c_s[K + 32] | xD[2][slots][32] | sred[256] | sumL[16] | bad[16] | full[8] | empty[8]
-    // (c_s carries 32 spare entries: the masked variants fetch constants of up to 31 rows they do not own)
-    size_t b = 256 + ((size_t)K + 32) * 8 + 2 * (size_t)fused_slots(CL) * 32 * 8 + 256 * 8 + 128 + 128 + 64 + 64;
+__host__ __device__ inline size_t fused_smem_header(int K, int CL, int M = 1) {
+    // tab[32] | c_s[M][K + 32] | xD[2][M][slots][32] | sred[M][256] | sumL[M][16] | bad[M][32] | full[8] | empty[8]
+    // (c_s carries 32 spare entries: the masked variants fetch constants of up to 31 rows they do not own;
+    //  M = 2: a second candidate f-vector is evaluated on the same staged tiles)
+    size_t b = 256 + (size_t)M * (((size_t)K + 32) * 8 + 2 * (size_t)fused_slots(CL) * 32 * 8 + 256 * 8 + 128 + 128) +
+               64 + 64;
     return (b + 127) & ~(size_t)127;
 }
 
@@ -193,8 +195,14 @@ __device__ __forceinline__ void cluster_barrier() {
 // WST: the launch also materialises the weights N_k W_nk = e_kn / D_n for the Hessian kernels (tile-major like
 // u_kn, every 256-byte row XOR-swizzled for the DMMA fragment loads): the values sit in registers at that
 // point, so the Newton half of an iteration costs one extra HBM write instead of a separate read+exp+write sweep.
-template <int R, bool FULL, int CW, int BATCH, int MODE, int CL, bool WST = false>
+// M = 2 (candidate-batched pass, SURVEY.md 8b `mbar_pass(ctx, M, f[M][K], ...)`): a second candidate vector is
+// evaluated on the SAME staged tile.  With the multiplicative state constant the expensive part, e0 = exp(-u'),
+// does not depend on f at all: the second candidate costs one more FMA per entry for its denominator
+// (D2 += E2_k e0) and one for its accumulator — 13 instead of 2 x 11 fp64 operations per entry, and one read of
+// u_kn instead of two.  It needs a second accumulator set, so it runs with <= 16 states per thread.
+template <int R, bool FULL, int CW, int BATCH, int MODE, int CL, bool WST = false, int M = 1>
 __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParams p) {
+    static_assert(M == 1 || ((MODE & 2) && R <= 16 && !WST), "M = 2 needs the multiplicative constant and R <= 16");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // device-resident loops: a converged (or failed) solver turns the rest of the enqueued batch into no-ops.
     // `done` is only written by the last CTA of a launch, after every CTA has taken its ticket, so all CTAs
@@ -207,14 +215,15 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
     const unsigned nGroups = gridDim.x / CL, grp = blockIdx.x / CL;      // CTA (pair) index
     double* tab = reinterpret_cast<double*>(smem_raw);
     double* c_s = tab + 32;
-    double* xD = c_s + K + 32;                   // [2][slots][32]
+    double* c_s2 = c_s + (K + 32);               // constants of the second candidate (M == 2)
+    double* xD = c_s + M * (K + 32);             // [2][M][slots][32]
     constexpr int SLOTS = fused_slots(CL);
-    double* sred = xD + 2 * SLOTS * 32;          // [Wn][K]  (Wn * K <= 256)
-    double* s_sumL = sred + 256;                 // [16]
-    int* s_bad = reinterpret_cast<int*>(s_sumL + 16);         // [16] (+pad)
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_sumL + 32);
+    double* sred = xD + 2 * M * SLOTS * 32;      // [M][Wn][K]  (Wn * K <= 256)
+    double* s_sumL = sred + M * 256;             // [M][16]
+    int* s_bad = reinterpret_cast<int*>(s_sumL + M * 16);     // [M][32]
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_sumL + M * 32);
     uint64_t* bar_empty = bar_full + 8;
-    unsigned char* stages = smem_raw + fused_smem_header(K, CL);
+    unsigned char* stages = smem_raw + fused_smem_header(K, CL, M);
     __shared__ bool s_last;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -224,7 +233,11 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
         c_s[k] = (MODE & 2) ? exp(p.c[kbase + k]) : p.c[kbase + k];
     // masked variants read up to 31 state constants past this CTA's rows: keep those entries finite
     for (int i = threadIdx.x; i < 32; i += blockDim.x) c_s[Kl + i] = 0.0;
-    for (int i = threadIdx.x; i < 2 * SLOTS * 32; i += blockDim.x) xD[i] = 0.0;
+    if constexpr (M == 2) {
+        for (int k = threadIdx.x; k < Kl; k += blockDim.x) c_s2[k] = exp(p.c2[kbase + k]);
+        for (int i = threadIdx.x; i < 32; i += blockDim.x) c_s2[Kl + i] = 0.0;
+    }
+    for (int i = threadIdx.x; i < 2 * M * SLOTS * 32; i += blockDim.x) xD[i] = 0.0;
     // lane-replicated exp table, 8 KB aligned so that its address bits never overlap the index bits
     const uint32_t tabRep = (smem_u32(stages + (size_t)p.NS * p.stageBytes) + 8191u) & ~8191u;
     if (MODE & 1)
@@ -244,10 +257,13 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
 
     const int tilesPerStage = p.Wn * p.TPW;
     double acc[R];
+    double acc2[M == 2 ? R : 1];
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[r] = 0.0;
-    double sumL = 0.0;
-    int bad = 0;
+#pragma unroll
+    for (int r = 0; r < (M == 2 ? R : 1); ++r) acc2[r] = 0.0;
+    double sumL = 0.0, sumL2 = 0.0;
+    int bad = 0, bad2 = 0;
     const int g = warp / p.Wk, w = warp % p.Wk;   // sample group, state chunk (consumers)
     const int k0 = w * p.Rw;
 
@@ -296,6 +312,8 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
         int it = 0;
         double mprod = 1.0;   // running product of the mantissas of D_n (see logprod_push)
         int esum = 0, npush = 0;
+        double mprod2 = 1.0;
+        int esum2 = 0;
         TabRef tr;
         tr.hi = __double2hiint(MBAR_EXP_TABLE[lane]);
         tr.lo = __double2loint(MBAR_EXP_TABLE[lane]);
@@ -332,26 +350,46 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                     }
                     exp_rows<R, B, 0, MODE, !FULL>(cA, uA, cB, uB, tr, e, Dp, c_s + k0, tp, actbits);
                 }
-                double D = Dp;
+                double D = Dp, D2 = 0.0, Dp2 = 0.0;
+                if constexpr (M == 2) {
+                    // second candidate's partial denominator from the same e0 (state constants: broadcast loads)
+#pragma unroll
+                    for (int r = 0; r < R; ++r) Dp2 = fma(lds_f64(c_s2 + k0 + r), e[r], Dp2);
+                    D2 = Dp2;
+                }
                 if (CL > 1) {
                     // CL*8 partial sums per sample: slot = owner rank * 8 + warp, written locally and into
                     // every partner CTA's shared memory; all CTAs then add them in the same order
-                    double* x = xD + (par * SLOTS + half * 8 + w) * 32 + lane;
+                    double* x = xD + (par * M * SLOTS + half * 8 + w) * 32 + lane;
                     *x = Dp;
+                    if constexpr (M == 2) x[SLOTS * 32] = Dp2;
 #pragma unroll
-                    for (int q = 1; q < CL; ++q) st_cluster_f64(x, (unsigned)((half + q) % CL), Dp);
+                    for (int q = 1; q < CL; ++q) {
+                        st_cluster_f64(x, (unsigned)((half + q) % CL), Dp);
+                        if constexpr (M == 2) st_cluster_f64(x + SLOTS * 32, (unsigned)((half + q) % CL), Dp2);
+                    }
                     cluster_barrier();
-                    const double* xs = xD + par * SLOTS * 32 + lane;
+                    const double* xs = xD + par * M * SLOTS * 32 + lane;
                     D = 0.0;
 #pragma unroll
                     for (int ww = 0; ww < CL * 8; ++ww) D += xs[ww * 32];
+                    if constexpr (M == 2) {
+                        D2 = 0.0;
+#pragma unroll
+                        for (int ww = 0; ww < CL * 8; ++ww) D2 += xs[(SLOTS + ww) * 32];
+                    }
                     par ^= 1;
                 } else if (p.Wk > 1) {
-                    double* x = xD + (par * CW + g * p.Wk) * 32 + lane;
+                    double* x = xD + (par * M * SLOTS + g * p.Wk) * 32 + lane;
                     x[w * 32] = Dp;
+                    if constexpr (M == 2) x[(SLOTS + w) * 32] = Dp2;
                     named_bar_sync(1 + g, p.Wk * 32);
                     D = 0.0;
                     for (int ww = 0; ww < p.Wk; ++ww) D += x[ww * 32];
+                    if constexpr (M == 2) {
+                        D2 = 0.0;
+                        for (int ww = 0; ww < p.Wk; ++ww) D2 += x[(SLOTS + ww) * 32];
+                    }
                     par ^= 1;
                 }
                 const bool valid = tile * TILE_N + lane < p.N;
@@ -360,6 +398,13 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                 const double invD = valid ? (FULL ? rD : rD * wn) : 0.0;
 #pragma unroll
                 for (int r = 0; r < R; ++r) acc[r] = fma(e[r], invD, acc[r]);
+                if constexpr (M == 2) {
+                    if (valid && !(D2 > 1e-250 && D2 < 1e250)) bad2 = 1;
+                    const double rD2 = 1.0 / D2;
+                    const double invD2 = valid ? (FULL ? rD2 : rD2 * wn) : 0.0;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) acc2[r] = fma(e[r], invD2, acc2[r]);
+                }
                 if (WST) {
                     // weights of this lane's sample, rows of this warp (bootstrap multiplicities enter the
                     // second moments as sqrt(w_n) on both factors)
@@ -379,9 +424,14 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                     if (valid) {
                         if (!FULL && p.wgt) {
                             sumL += wn * log(D);          // general multiplicities: one log per sample
+                            if constexpr (M == 2) sumL2 += wn * log(D2);
                         } else {
                             logprod_push(D, mprod, esum);
-                            if ((++npush & 255) == 0) logprod_renorm(mprod, esum);
+                            if constexpr (M == 2) logprod_push(D2, mprod2, esum2);
+                            if ((++npush & 255) == 0) {
+                                logprod_renorm(mprod, esum);
+                                if constexpr (M == 2) logprod_renorm(mprod2, esum2);
+                            }
                         }
                     }
                     if (p.Lout) p.Lout[tile * TILE_N + lane] = log(D) + p.mid;
@@ -404,15 +454,35 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
             s_sumL[warp] = (w == 0 && half == 0) ? sumL : 0.0;
             s_bad[warp] = bad;
         }
+        if constexpr (M == 2) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const double t = warp_sum(acc2[r]);
+                if (lane == 0 && r < p.Rw && k0 + r < Kl) sred[256 + g * Kl + k0 + r] = t;
+            }
+            sumL2 += (double)esum2 * 0.693147180559945309417232 + log(mprod2);
+            sumL2 = warp_sum(sumL2);
+            bad2 = __any_sync(0xffffffffu, bad2);
+            if (lane == 0) {
+                s_sumL[16 + warp] = (w == 0 && half == 0) ? sumL2 : 0.0;
+                s_bad[32 + warp] = bad2;
+            }
+        }
     }
     if (CL > 1) cluster_barrier();    // a partner may not exit while it can still be written to
     __syncthreads();
 
-    double* P = p.partial + (size_t)grp * (K + 2);
+    constexpr int PW = M;                               // partial blocks of K + 2 doubles per CTA group
+    double* P = p.partial + (size_t)grp * (PW * (K + 2));
     for (int k = threadIdx.x; k < Kl; k += blockDim.x) {
         double t = 0.0;
         for (int gg = 0; gg < p.Wn; ++gg) t += sred[gg * Kl + k];
         P[kbase + k] = t;
+        if constexpr (M == 2) {
+            double t2 = 0.0;
+            for (int gg = 0; gg < p.Wn; ++gg) t2 += sred[256 + gg * Kl + k];
+            P[K + 2 + kbase + k] = t2;
+        }
     }
     if (threadIdx.x == 0 && half == 0) {
         double t = 0.0;
@@ -423,6 +493,16 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
         }
         P[K] = t;
         P[K + 1] = (double)b;
+        if constexpr (M == 2) {
+            double t2 = 0.0;
+            int b2 = 0;
+            for (int i = 0; i < CW; ++i) {
+                t2 += s_sumL[16 + i];
+                b2 |= s_bad[32 + i];
+            }
+            P[K + 2 + K] = t2;
+            P[K + 2 + K + 1] = (double)b2;
+        }
     }
     __threadfence();
     __syncthreads();
@@ -436,11 +516,14 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
     const PassLayout lay{K};
     // ---- last CTA: deterministic reduction over CTAs, optional exchange with the other GPUs, optional
     // ---- self-consistent epilogue (f <- f - log S, gauge, c for the next launch): one kernel per iteration
-    double* tot = reinterpret_cast<double*>(stages);     // [K + 2] (the ring is idle now)
-    for (int k = threadIdx.x; k < K + 2; k += blockDim.x) {
+    double* tot = reinterpret_cast<double*>(stages);     // [M][K + 2] (the ring is idle now)
+    constexpr int TW = M;
+    const int totN = TW * (K + 2);
+    for (int k = threadIdx.x; k < totN; k += blockDim.x) {
         double t = 0.0;
-        for (unsigned b = 0; b < nGroups; ++b) t += p.partial[(size_t)b * (K + 2) + k];
+        for (unsigned b = 0; b < nGroups; ++b) t += p.partial[(size_t)b * totN + k];
         if (k == K) t += p.sumW * p.mid;
+        if (M == 2 && k == K + 2 + K) t += p.sumW * p.mid2;
         tot[k] = t;
     }
     __syncthreads();
@@ -455,8 +538,8 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
         const int par = (int)(seq & 1ull);
         const int P = p.peer.nranks, me = p.peer.rank;
         for (int q = 0; q < P; ++q) {
-            double* dst = p.peer.inbox[q] + ((size_t)par * P + me) * (K + 2);
-            for (int k = threadIdx.x; k < K + 2; k += blockDim.x) dst[k] = tot[k];
+            double* dst = p.peer.inbox[q] + ((size_t)par * P + me) * totN;
+            for (int k = threadIdx.x; k < totN; k += blockDim.x) dst[k] = tot[k];
         }
         __threadfence_system();
         __syncthreads();
@@ -485,14 +568,17 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
             }
         }
         __syncthreads();
-        const double* in = p.peer.inbox[me] + (size_t)par * P * (K + 2);
-        for (int k = threadIdx.x; k < K + 2; k += blockDim.x) {
+        const double* in = p.peer.inbox[me] + (size_t)par * P * totN;
+        for (int k = threadIdx.x; k < totN; k += blockDim.x) {
             double t = 0.0;
-            for (int q = 0; q < P; ++q) t += __ldcv(in + (size_t)q * (K + 2) + k);
+            for (int q = 0; q < P; ++q) t += __ldcv(in + (size_t)q * totN + k);
             tot[k] = t;
         }
         __syncthreads();
-        if (threadIdx.x == 0 && s_timeout) tot[K + 1] += 1.0e6;   // flag > 0 -> host reports the failure
+        if (threadIdx.x == 0 && s_timeout) {
+            tot[K + 1] += 1.0e6;   // flag > 0 -> host reports the failure
+            if (M == 2) tot[K + 2 + K + 1] += 1.0e6;
+        }
         __syncthreads();
     }
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
@@ -507,6 +593,19 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
     if (threadIdx.x == 0) {
         p.out[lay.sumL()] = tot[K];
         p.out[lay.flag()] = tot[K + 1];
+    }
+    if constexpr (M == 2) {
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const bool act = (p.rowmask[k >> 6] >> (k & 63)) & 1ull;
+            double t = tot[K + 2 + k];
+            if (act) t *= exp(p.c2[k]);
+            p.out2[lay.S() + k] = act ? t / p.Nk[k] : 0.0;
+            p.out2[lay.logS() + k] = 0.0;
+        }
+        if (threadIdx.x == 0) {
+            p.out2[lay.sumL()] = tot[K + 2 + K];
+            p.out2[lay.flag()] = tot[K + 2 + K + 1];
+        }
     }
     if (p.epi) {
         __syncthreads();
@@ -590,7 +689,7 @@ bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, bool allState
 
 // Configure the fused kernel for f (host) and stage c = f + log N - mid on the device.
 int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, FusedParams* out,
-                  bool* ok, double* d_cdst, double* h_stage, bool wantW) {
+                  bool* ok, double* d_cdst, double* h_stage, bool wantW, int M) {
     if (!d_cdst) d_cdst = ctx->d_c;
     if (!h_stage) h_stage = ctx->h_f;
     *ok = false;
@@ -606,9 +705,14 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allSta
     mode |= 1;   // the shuffle-gathered table (bit 0 clear) was measured 10 % slower and is retired
     if (spread > 600.0) mode &= 1;   // exp(c_k) * exp(-u') needs the spread inside the exponent range
     p.allStates = allStates ? 1 : 0;
+    p.M = M;
+    // two candidates per launch: second accumulator set -> at most 16 states per thread, hence K <= 1024, and the
+    // e0 = exp(-u') sharing needs the multiplicative constant; the caller falls back to two launches otherwise
+    if (M == 2 && (!(mode & 2) || K > 1024 || K < 2 || allStates || wantW)) return MBAR_B200_OK;
     const int cw = 8;
-    const int rmax = 32;
-    p.CL = K > 1024 ? 8 : K > 512 ? 4 : K > 256 ? 2 : 1;   // clusters of CL CTAs, K/CL states each
+    const int rmax = (M == 2) ? 16 : 32;
+    const int perCta = cw * rmax;                          // states one CTA can hold
+    p.CL = K > 4 * perCta ? 8 : K > 2 * perCta ? 4 : K > perCta ? 2 : 1;   // clusters of CL CTAs, K/CL states each
     p.Kh = (K + p.CL - 1) / p.CL;
     if (p.CL > 1) p.Kh = (p.Kh + 1) & ~1;   // even split point: 16-byte aligned pairs of state constants
     int wk = 1;
@@ -634,7 +738,7 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allSta
         if (over > 0) p.stageBytes += (uint32_t)over * TILE_N * 8;
         p.stageBytes = (p.stageBytes + 127u) & ~127u;
     }
-    const size_t header = fused_smem_header(K, p.CL);
+    const size_t header = fused_smem_header(K, p.CL, M);
     int ns = (int)((225 * 1024 - header - 16384) / p.stageBytes);   // (CL >= 4 -> 2 stages of 64 KB)
     p.NS = ns > 8 ? 8 : ns;
     if (p.NS < 2) return MBAR_B200_OK;
@@ -670,7 +774,7 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allSta
 
 // Launch with whatever c currently sits in ctx->d_c (device-resident iteration).
 int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
-    const size_t smem = fused_smem_header(p.K, p.CL) + (size_t)p.NS * p.stageBytes + 16384;
+    const size_t smem = fused_smem_header(p.K, p.CL, p.M) + (size_t)p.NS * p.stageBytes + 16384;
     int64_t grid = p.nStages < ctx->smCount / p.CL ? p.nStages : ctx->smCount / p.CL;
     grid *= p.CL;
     const int Rt = p.Rw <= 8 ? 8 : p.Rw <= 16 ? 16 : 32;
@@ -692,18 +796,32 @@ int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
         else if (!(p.mode & 2)) { kern = pass_fused_kernel<32, true, 8, 8, 1, CL_, true>; which = ID_ + 2; } \
         else { kern = pass_fused_kernel<32, true, 8, 8, 3, CL_, true>; which = ID_ + 3; }                    \
     }
-    PICK(8, 1, 0) PICK(16, 1, 4) PICK(32, 1, 8) PICK(32, 2, 12) PICK(32, 4, 16) PICK(32, 8, 20)
-    PICKW(1, 24) PICKW(2, 28) PICKW(4, 32) PICKW(8, 36)
+#define PICKM(R_, CL_, ID_)                                                                          \
+    if (Rt == R_ && p.CL == CL_) {                                                                   \
+        if (!full) { kern = pass_fused_kernel<R_, false, 8, 8, 3, CL_, false, 2>; which = ID_; }     \
+        else { kern = pass_fused_kernel<R_, true, 8, 8, 3, CL_, false, 2>; which = ID_ + 1; }        \
+    }
+    if (p.M == 2) {
+        MBAR_REQUIRE((p.mode & 2) && !p.Wout && p.c2 && p.out2, MBAR_B200_ERR_INVALID, "bad M = 2 launch");
+        PICKM(8, 1, 40) PICKM(16, 1, 42) PICKM(16, 2, 44) PICKM(16, 4, 46) PICKM(16, 8, 48)
+    } else {
+        PICK(8, 1, 0) PICK(16, 1, 4) PICK(32, 1, 8) PICK(32, 2, 12) PICK(32, 4, 16) PICK(32, 8, 20)
+        PICKW(1, 24) PICKW(2, 28) PICKW(4, 32) PICKW(8, 36)
+    }
+#undef PICKM
 #undef PICKW
 #undef PICK
     MBAR_REQUIRE(kern, MBAR_B200_ERR_INVALID, "no fused kernel variant for K=%d", p.K);
-    MBAR_REQUIRE(!p.Wout || which >= 24, MBAR_B200_ERR_INVALID, "no weight-storing fused variant for K=%d", p.K);
+    MBAR_REQUIRE(!p.Wout || (which >= 24 && which < 40), MBAR_B200_ERR_INVALID,
+                 "no weight-storing fused variant for K=%d", p.K);
     snprintf(ctx->lastKernel, sizeof(ctx->lastKernel),
              "pass_fused_kernel<R=%d, %s, CW=8, BATCH=8, MODE=%d (%s), CL=%d%s> grid=%lld NS=%d TPW=%d", Rt,
              full ? "FULL" : "MASKED", (p.mode & 2) ? 3 : 1,
              (p.mode & 2) ? "LDS table + multiplicative state constant" : "LDS table", p.CL,
-             (which >= 24) ? ", WST (weights stored for the Hessian)" : "", (long long)grid, p.NS, p.TPW);
-    static size_t attrSetAll[16][40] = {{0}};          // per device: the attribute belongs to the context
+             (which >= 40) ? ", M=2 (two candidates per launch)"
+                           : (which >= 24) ? ", WST (weights stored for the Hessian)" : "",
+             (long long)grid, p.NS, p.TPW);
+    static size_t attrSetAll[16][52] = {{0}};          // per device: the attribute belongs to the context
     size_t* attrSet = attrSetAll[ctx->device & 15];
     if (attrSet[which] < smem) {
         MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

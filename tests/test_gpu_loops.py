@@ -235,3 +235,32 @@ def test_hessian_beyond_2048_states(lib):
         H = p.hessian(f)
         H_ref = orc.mbar_hessian(u, N_k, f)
         np.testing.assert_allclose(H, H_ref, rtol=1e-9, atol=1e-11 * np.max(np.abs(H_ref)))
+
+
+@pytest.mark.parametrize("K", [2, 5, 16, 31, 64, 100, 128, 200, 256, 300, 512, 700, 1024])
+def test_candidate_batched_pass_kernel(lib, K):
+    """pass_fused_kernel<..., M = 2>: two candidate vectors on the same staged tile (single CTA up to K = 128,
+    clusters of 2 / 4 / 8 CTAs above), against two single-candidate launches and the oracle."""
+    empty = () if K < 5 else (2,)
+    u, N_k, f = _random_problem(K, (40 if K < 300 else 6) * K, seed=500 + K, empty=empty)
+    s = N_k > 0
+    rng = np.random.RandomState(K)
+    f2 = np.stack([f, f + rng.normal(scale=0.3, size=K)])
+    f2[:, ~s] = 0.0
+    with lib.DeviceProblem(u, N_k) as p:
+        S, sumL = p.pass_multi(f2)
+        assert "M=2" in p.last_kernels()["pass_kernel"], p.last_kernels()
+        for m in range(2):
+            S1, sumL1, _ = p.streaming_pass(f2[m])
+            np.testing.assert_allclose(S[m], S1, rtol=1e-12, atol=1e-300)
+            np.testing.assert_allclose(sumL[m], sumL1, rtol=1e-13)
+            S_ref, L_ref = orc.single_pass_sums(u[s], N_k[s], f2[m][s])
+            np.testing.assert_allclose(S[m][s], S_ref, rtol=1e-11)
+            np.testing.assert_allclose(sumL[m], L_ref.sum(), rtol=1e-12)
+        # bootstrap multiplicities ride through the batched kernel too (masked family)
+        w = rng.poisson(1.0, size=u.shape[1]).astype(float)
+        p.set_sample_weights(w)
+        Sw, sumLw = p.pass_multi(f2)
+        S1, sumL1, _ = p.streaming_pass(f2[1])
+        np.testing.assert_allclose(Sw[1], S1, rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(sumLw[1], sumL1, rtol=1e-13)
