@@ -435,7 +435,10 @@ hessian_big_reduce_kernel(const double* __restrict__ Gpart, int K, const HessSpl
 // Ring of NSLOT one-tile slots (K*256 bytes, one bulk copy each).  Pair q of the CTA takes local tiles q, q+4,
 // q+8, ...; NSLOT is a multiple of 4, so a pair always reuses its own slots and the even warp of the pair can
 // refill a slot as soon as both warps have released it: no CTA-wide barrier in the loop.
-template <int KT>
+// WIN: the tiles come from the weight buffer the fused pass filled (FusedParams::Wout: N_k W_nk, rows
+// XOR-swizzled) — no exp, conflict-free fragment loads, the DMMA pipe has the fp64 datapath to itself; otherwise
+// they are energies and every lane converts the entries of its own fragment.
+template <int KT, bool WIN>
 __global__ void __launch_bounds__(256, 1)
 hessian_small_kernel(const double* __restrict__ u, const double* __restrict__ Lp, const double* __restrict__ c,
                      const unsigned long long* __restrict__ rowmask, int K, int64_t N, int64_t nTiles, int NSLOT,
@@ -480,8 +483,8 @@ hessian_small_kernel(const double* __restrict__ u, const double* __restrict__ Lp
 #pragma unroll
     for (int mt = 0; mt < KT; ++mt) {
         const int k = mt * 8 + fragRow;
-        const bool a = k < K && ((rowmask[k >> 6] >> (k & 63)) & 1ull);
-        cr[mt] = a ? c[k] : 0.0;
+        const bool a = k < K && (WIN || ((rowmask[k >> 6] >> (k & 63)) & 1ull));
+        cr[mt] = (a && !WIN) ? c[k] : 0.0;
         act |= (uint32_t)a << mt;
     }
     double acc[NT][2];
@@ -492,22 +495,35 @@ hessian_small_kernel(const double* __restrict__ u, const double* __restrict__ Lp
         const int slot = j % NSLOT;
         const uint32_t par = (uint32_t)(j / NSLOT) & 1u;
         const int64_t tile = t0 + j;
-        const double Lt = Lp[tile * TILE_N + lane];
-        const double swt = sqrtw ? sqrtw[tile * TILE_N + lane] : 1.0;
+        double Lt = 0.0, swt = 1.0;
+        if (!WIN) {
+            Lt = Lp[tile * TILE_N + lane];
+            if (sqrtw) swt = sqrtw[tile * TILE_N + lane];
+        }
         mbar_wait(smem_u32(&bar_full[slot]), par);
         const double* P = reinterpret_cast<const double*>(ring + (size_t)slot * slotBytes);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-            const int s = (4 * h + kk) * 4 + fragCol;          // sample of this lane's fragment column
-            const double L = __shfl_sync(0xffffffffu, Lt, s);
-            const double sw = __shfl_sync(0xffffffffu, swt, s);
-            const bool valid = tile * TILE_N + s < N;
+            const int ks = 4 * h + kk;
+            const int s = ks * 4 + fragCol;                    // sample of this lane's fragment column
             double a[KT];
+            if (WIN) {
+                const int col = ((ks ^ fragRow) << 2) + fragCol;   // (4 ks + fragCol) ^ (fragRow << 2)
 #pragma unroll
-            for (int mt = 0; mt < KT; ++mt) {
-                const double v = P[(mt * 8 + fragRow) * TILE_N + s];
-                const double e = sw * exp_fast(fmin(fmax(cr[mt] - v - L, -800.0), 700.0), tab);
-                a[mt] = (valid && ((act >> mt) & 1u)) ? e : 0.0;     // select: garbage rows (k >= K) never count
+                for (int mt = 0; mt < KT; ++mt) {
+                    const double v = P[(mt * 8 + fragRow) * TILE_N + col];
+                    a[mt] = ((act >> mt) & 1u) ? v : 0.0;      // rows >= K of the slot were never loaded
+                }
+            } else {
+                const double L = __shfl_sync(0xffffffffu, Lt, s);
+                const double sw = __shfl_sync(0xffffffffu, swt, s);
+                const bool valid = tile * TILE_N + s < N;
+#pragma unroll
+                for (int mt = 0; mt < KT; ++mt) {
+                    const double v = P[(mt * 8 + fragRow) * TILE_N + s];
+                    const double e = sw * exp_fast(fmin(fmax(cr[mt] - v - L, -800.0), 700.0), tab);
+                    a[mt] = (valid && ((act >> mt) & 1u)) ? e : 0.0;     // select: garbage rows (k >= K) never count
+                }
             }
 #pragma unroll
             for (int mt = 0; mt < KT; ++mt)
@@ -609,25 +625,29 @@ int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, Loo
         if (grid < 1) grid = 1;
         MBAR_TRY(ensure_gpart(ctx, (size_t)grid * KP * KP * sizeof(double)));
         const size_t smem = 1024 + (size_t)nslot * slotBytes;
+        const bool win = weightsReady && !allRows && ctx->d_Wt;
         void (*kern)(const double*, const double*, const double*, const unsigned long long*, int, int64_t, int64_t,
                      int, double*, const double*, const LoopState*) =
-            KT == 2 ? hessian_small_kernel<2> : KT == 4 ? hessian_small_kernel<4> : hessian_small_kernel<8>;
-        static size_t attr[16][3] = {{0}};
-        size_t& a = attr[ctx->device & 15][KT == 2 ? 0 : KT == 4 ? 1 : 2];
+            win ? (KT == 2 ? hessian_small_kernel<2, true> : KT == 4 ? hessian_small_kernel<4, true>
+                                                                     : hessian_small_kernel<8, true>)
+                : (KT == 2 ? hessian_small_kernel<2, false> : KT == 4 ? hessian_small_kernel<4, false>
+                                                                      : hessian_small_kernel<8, false>);
+        static size_t attr[16][6] = {{0}};
+        size_t& a = attr[ctx->device & 15][(KT == 2 ? 0 : KT == 4 ? 1 : 2) + (win ? 3 : 0)];
         if (a < smem) {
             MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             a = smem;
         }
         MBAR_CUDA(cudaEventRecord(ctx->evH1, ctx->stream));
-        kern<<<(unsigned)grid, 256, smem, ctx->stream>>>(ctx->d_u, ctx->d_L, d_ch, mask, K, ctx->N, ctx->nTiles,
-                                                        nslot, ctx->d_W, ctx->d_sqrtw, loop);
+        kern<<<(unsigned)grid, 256, smem, ctx->stream>>>(win ? ctx->d_Wt : ctx->d_u, ctx->d_L, d_ch, mask, K, ctx->N,
+                                                        ctx->nTiles, nslot, ctx->d_W, ctx->d_sqrtw, loop);
         MBAR_CUDA(cudaGetLastError());
         hessian_small_reduce_kernel<<<(KP * KP + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_W, K, KP, (int)grid,
                                                                                     ctx->d_out + lay.G(), loop);
         MBAR_CUDA(cudaGetLastError());
         MBAR_CUDA(cudaEventRecord(ctx->evH2, ctx->stream));
-        snprintf(ctx->lastHessKernel, sizeof(ctx->lastHessKernel), "hessian_small_kernel<KT=%d> grid=%lld NSLOT=%d",
-                 KT, (long long)grid, nslot);
+        snprintf(ctx->lastHessKernel, sizeof(ctx->lastHessKernel), "hessian_small_kernel<KT=%d, %s> grid=%lld NSLOT=%d",
+                 KT, win ? "weights stored by the fused pass (WST)" : "in-register conversion", (long long)grid, nslot);
         ctx->launches += 2;
         ctx->passes++;
         return MBAR_B200_OK;

@@ -759,7 +759,7 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allSta
         MBAR_CUDA(cudaMalloc((void**)&ctx->d_L, (size_t)ctx->nTiles * TILE_N * sizeof(double)));
     p.Lout = wantL ? ctx->d_L : nullptr;
     // weights for the K > 64 Hessian path ride along when the caller is about to evaluate the Hessian at this f
-    p.Wout = (wantW && !allStates && K > 64 && ensure_weight_buffer(ctx)) ? ctx->d_Wt : nullptr;
+    p.Wout = (wantW && !allStates && M == 1 && ensure_weight_buffer(ctx)) ? ctx->d_Wt : nullptr;
     p.wgt = ctx->d_wgt;
     p.sumW = ctx->d_wgt ? ctx->sumW : (double)ctx->N;
     for (int k = 0; k < K; ++k)
@@ -789,12 +789,12 @@ int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
         else if (!(p.mode & 2)) { kern = pass_fused_kernel<R_, true, 8, 8, 1, CL_>; which = ID_ + 2; } \
         else { kern = pass_fused_kernel<R_, true, 8, 8, 3, CL_>; which = ID_ + 3; }                    \
     }
-#define PICKW(CL_, ID_)                                                                              \
-    if (Rt == 32 && p.CL == CL_ && p.Wout) {                                                         \
-        if (!full && !(p.mode & 2)) { kern = pass_fused_kernel<32, false, 8, 8, 1, CL_, true>; which = ID_; } \
-        else if (!full) { kern = pass_fused_kernel<32, false, 8, 8, 3, CL_, true>; which = ID_ + 1; }        \
-        else if (!(p.mode & 2)) { kern = pass_fused_kernel<32, true, 8, 8, 1, CL_, true>; which = ID_ + 2; } \
-        else { kern = pass_fused_kernel<32, true, 8, 8, 3, CL_, true>; which = ID_ + 3; }                    \
+#define PICKW(R_, CL_, ID_)                                                                          \
+    if (Rt == R_ && p.CL == CL_ && p.Wout) {                                                         \
+        if (!full && !(p.mode & 2)) { kern = pass_fused_kernel<R_, false, 8, 8, 1, CL_, true>; which = ID_; } \
+        else if (!full) { kern = pass_fused_kernel<R_, false, 8, 8, 3, CL_, true>; which = ID_ + 1; }        \
+        else if (!(p.mode & 2)) { kern = pass_fused_kernel<R_, true, 8, 8, 1, CL_, true>; which = ID_ + 2; } \
+        else { kern = pass_fused_kernel<R_, true, 8, 8, 3, CL_, true>; which = ID_ + 3; }                    \
     }
 #define PICKM(R_, CL_, ID_)                                                                          \
     if (Rt == R_ && p.CL == CL_) {                                                                   \
@@ -806,22 +806,22 @@ int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
         PICKM(8, 1, 40) PICKM(16, 1, 42) PICKM(16, 2, 44) PICKM(16, 4, 46) PICKM(16, 8, 48)
     } else {
         PICK(8, 1, 0) PICK(16, 1, 4) PICK(32, 1, 8) PICK(32, 2, 12) PICK(32, 4, 16) PICK(32, 8, 20)
-        PICKW(1, 24) PICKW(2, 28) PICKW(4, 32) PICKW(8, 36)
+        PICKW(32, 1, 24) PICKW(32, 2, 28) PICKW(32, 4, 32) PICKW(32, 8, 36) PICKW(16, 1, 52) PICKW(8, 1, 56)
     }
 #undef PICKM
 #undef PICKW
 #undef PICK
     MBAR_REQUIRE(kern, MBAR_B200_ERR_INVALID, "no fused kernel variant for K=%d", p.K);
-    MBAR_REQUIRE(!p.Wout || (which >= 24 && which < 40), MBAR_B200_ERR_INVALID,
+    MBAR_REQUIRE(!p.Wout || (which >= 24 && which < 40) || which >= 52, MBAR_B200_ERR_INVALID,
                  "no weight-storing fused variant for K=%d", p.K);
     snprintf(ctx->lastKernel, sizeof(ctx->lastKernel),
              "pass_fused_kernel<R=%d, %s, CW=8, BATCH=8, MODE=%d (%s), CL=%d%s> grid=%lld NS=%d TPW=%d", Rt,
              full ? "FULL" : "MASKED", (p.mode & 2) ? 3 : 1,
              (p.mode & 2) ? "LDS table + multiplicative state constant" : "LDS table", p.CL,
-             (which >= 40) ? ", M=2 (two candidates per launch)"
+             (which >= 40 && which < 52) ? ", M=2 (two candidates per launch)"
                            : (which >= 24) ? ", WST (weights stored for the Hessian)" : "",
              (long long)grid, p.NS, p.TPW);
-    static size_t attrSetAll[16][52] = {{0}};          // per device: the attribute belongs to the context
+    static size_t attrSetAll[16][60] = {{0}};          // per device: the attribute belongs to the context
     size_t* attrSet = attrSetAll[ctx->device & 15];
     if (attrSet[which] < smem) {
         MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

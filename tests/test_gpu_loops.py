@@ -108,8 +108,8 @@ def test_hessian_kernel_paths_vs_oracle(lib, K):
         np.testing.assert_allclose(H, H.T, rtol=0, atol=0)
         names = p.last_kernels()
         assert ("hessian_small_kernel" in names["hessian_kernel"]) == (K <= 64), names
-        if K > 64:   # the fused pass at this f stored the weights itself (no separate sweep)
-            assert "WST" in names["pass_kernel"] and "weights stored by the fused pass" in names["hessian_kernel"], names
+        # the fused pass at this f stored the weights itself (no separate sweep, no exp in the Hessian kernels)
+        assert "WST" in names["pass_kernel"] and "weights stored by the fused pass" in names["hessian_kernel"], names
         # all states (weight moments): unsampled rows switched on
         S, G = p.weight_moments(f)
         W = orc.mbar_W_nk(u, N_k, f)
