@@ -204,17 +204,23 @@ newton_kernel(double* __restrict__ Ag, int na, int K, const int* __restrict__ ac
     for (int j = 0; j < n; ++j) {
         for (int k = tid; k < j; k += nt) row[k] = LDM(M + (size_t)k * n + j);
         __syncthreads();
-        for (int i = j + tid; i < n; i += nt) {
-            double s0 = LDM(M + (size_t)j * n + i), s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int k = 0;
-            for (; k + 4 <= j; k += 4) {
+        // row i of the update is a dot product of length j: four lanes share it (k = ks, ks + 4, ...) so that a
+        // column keeps 4 (n - j) threads busy instead of n - j — the loop is bound by the latency of its loads
+        for (int base = j; base < n; base += (nt >> 2)) {     // trip count uniform over the CTA (full-mask shuffles)
+            const int i0 = base + (tid >> 2);
+            const int i = i0 < n ? i0 : n - 1;          // (idle quads recompute the last row)
+            const int ks = tid & 3;
+            double s0 = 0.0, s1 = 0.0;
+            int k = ks;
+            for (; k + 4 < j; k += 8) {
                 s0 = fma(-LDM(M + (size_t)k * n + i), row[k], s0);
-                s1 = fma(-LDM(M + (size_t)(k + 1) * n + i), row[k + 1], s1);
-                s2 = fma(-LDM(M + (size_t)(k + 2) * n + i), row[k + 2], s2);
-                s3 = fma(-LDM(M + (size_t)(k + 3) * n + i), row[k + 3], s3);
+                s1 = fma(-LDM(M + (size_t)(k + 4) * n + i), row[k + 4], s1);
             }
-            for (; k < j; ++k) s0 = fma(-LDM(M + (size_t)k * n + i), row[k], s0);
-            M[(size_t)j * n + i] = (s0 + s1) + (s2 + s3);
+            if (k < j) s0 = fma(-LDM(M + (size_t)k * n + i), row[k], s0);
+            double t = s0 + s1;
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            if (ks == 0 && i0 < n) M[(size_t)j * n + i] = LDM(M + (size_t)j * n + i) + t;
         }
         __syncthreads();
         const double d = LDM(M + (size_t)j * n + j);
@@ -530,7 +536,7 @@ static int enqueue_adaptive_iteration(mbar_b200_ctx* c, const FusedParams& pF, c
         a = shBytes;
     }
     const int bgrid = (int)std::min<int64_t>(((int64_t)n * n + 255) / 256, 4 * c->smCount);
-    const int nthreads = n >= 512 ? 1024 : n >= 128 ? 512 : 256;
+    const int nthreads = n >= 96 ? 1024 : n >= 32 ? 512 : 256;
     for (int attempt = 0; attempt < 2; ++attempt) {
         newton_build_kernel<<<bgrid, 256, 0, c->stream>>>(c->d_out + lay.G(), av, c->d_active, na, K, c->d_A,
                                                          attempt ? 1.0e-10 : 0.0, attempt, c->d_loop);
