@@ -571,33 +571,45 @@ int mbar_b200_create(mbar_b200_ctx** out, int device, int32_t K, int64_t N_local
     ALLOC(c->d_active, (size_t)K * sizeof(int));
     ALLOC(c->d_seq, sizeof(unsigned long long));
 #undef ALLOC
-    MBAR_CUDA(cudaHostAlloc((void**)&c->h_loop, sizeof(mbar::LoopState), cudaHostAllocDefault));
-    MBAR_CUDA(cudaMemset(c->d_loop, 0, sizeof(mbar::LoopState)));
-    MBAR_CUDA(cudaMemset(c->d_seq, 0, sizeof(unsigned long long)));
-    MBAR_CUDA(cudaMemcpy(c->d_active, c->active.data(), c->active.size() * sizeof(int), cudaMemcpyHostToDevice));
-    MBAR_CUDA(cudaEventCreate(&c->evH0));
-    MBAR_CUDA(cudaEventCreate(&c->evH1));
-    MBAR_CUDA(cudaEventCreate(&c->evH2));
-    MBAR_CUDA(cudaHostAlloc((void**)&c->h_out, (size_t)lay.size(true) * sizeof(double), cudaHostAllocDefault));
-    MBAR_CUDA(cudaHostAlloc((void**)&c->h_f, 8 * (size_t)K * sizeof(double), cudaHostAllocDefault));
-    MBAR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    MBAR_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
-    MBAR_CUDA(cudaEventCreate(&c->evA));
-    MBAR_CUDA(cudaEventCreate(&c->evB));
-    MBAR_CUDA(cudaEventCreateWithFlags(&c->evCopy[0], cudaEventDisableTiming));
-    MBAR_CUDA(cudaEventCreateWithFlags(&c->evCopy[1], cudaEventDisableTiming));
-    MBAR_CUDA(cudaMemcpy(c->d_Nk, N_k, (size_t)K * sizeof(double), cudaMemcpyHostToDevice));
+    // failures past this point must release what was allocated above
+#define CREATE_CUDA(call)                                                                   \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,                  \
+                      cudaGetErrorString(e__));                                             \
+            mbar_b200_destroy(c);                                                           \
+            return MBAR_B200_ERR_CUDA;                                                      \
+        }                                                                                   \
+    } while (0)
+    CREATE_CUDA(cudaHostAlloc((void**)&c->h_loop, sizeof(mbar::LoopState), cudaHostAllocDefault));
+    CREATE_CUDA(cudaMemset(c->d_loop, 0, sizeof(mbar::LoopState)));
+    CREATE_CUDA(cudaMemset(c->d_seq, 0, sizeof(unsigned long long)));
+    CREATE_CUDA(cudaMemcpy(c->d_active, c->active.data(), c->active.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CREATE_CUDA(cudaEventCreate(&c->evH0));
+    CREATE_CUDA(cudaEventCreate(&c->evH1));
+    CREATE_CUDA(cudaEventCreate(&c->evH2));
+    CREATE_CUDA(cudaHostAlloc((void**)&c->h_out, (size_t)lay.size(true) * sizeof(double), cudaHostAllocDefault));
+    CREATE_CUDA(cudaHostAlloc((void**)&c->h_f, 8 * (size_t)K * sizeof(double), cudaHostAllocDefault));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaEventCreate(&c->evA));
+    CREATE_CUDA(cudaEventCreate(&c->evB));
+    CREATE_CUDA(cudaEventCreateWithFlags(&c->evCopy[0], cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&c->evCopy[1], cudaEventDisableTiming));
+    CREATE_CUDA(cudaMemcpy(c->d_Nk, N_k, (size_t)K * sizeof(double), cudaMemcpyHostToDevice));
     {
         std::vector<double> eff(K);
         for (int k = 0; k < K; ++k) eff[k] = std::exp(c->h_logNkEff[k]);
-        MBAR_CUDA(cudaMemcpy(c->d_NkEff, eff.data(), (size_t)K * sizeof(double), cudaMemcpyHostToDevice));
+        CREATE_CUDA(cudaMemcpy(c->d_NkEff, eff.data(), (size_t)K * sizeof(double), cudaMemcpyHostToDevice));
     }
-    MBAR_CUDA(cudaMemcpy(c->d_rowmask, mask.data(), mask.size() * sizeof(unsigned long long),
+    CREATE_CUDA(cudaMemcpy(c->d_rowmask, mask.data(), mask.size() * sizeof(unsigned long long),
                          cudaMemcpyHostToDevice));
-    MBAR_CUDA(cudaMemset(c->d_zeromask, 0, mask.size() * sizeof(unsigned long long)));
-    MBAR_CUDA(cudaMemset(c->d_onesmask, 0xff, mask.size() * sizeof(unsigned long long)));
-    MBAR_CUDA(cudaMemset(c->d_ticket, 0, 4 * sizeof(unsigned int)));
-    MBAR_CUDA(cudaMemset(c->d_flag, 0, 4 * sizeof(int)));
+    CREATE_CUDA(cudaMemset(c->d_zeromask, 0, mask.size() * sizeof(unsigned long long)));
+    CREATE_CUDA(cudaMemset(c->d_onesmask, 0xff, mask.size() * sizeof(unsigned long long)));
+    CREATE_CUDA(cudaMemset(c->d_ticket, 0, 4 * sizeof(unsigned int)));
+    CREATE_CUDA(cudaMemset(c->d_flag, 0, 4 * sizeof(int)));
+#undef CREATE_CUDA
     *out = c;
     return MBAR_B200_OK;
 }
