@@ -589,7 +589,10 @@ int mbar_b200_create(mbar_b200_ctx** out, int device, int32_t K, int64_t N_local
     CREATE_CUDA(cudaEventCreate(&c->evH0));
     CREATE_CUDA(cudaEventCreate(&c->evH1));
     CREATE_CUDA(cudaEventCreate(&c->evH2));
-    CREATE_CUDA(cudaHostAlloc((void**)&c->h_out, (size_t)lay.size(true) * sizeof(double), cudaHostAllocDefault));
+    // (holds one packed result with G, or the two candidate results of mbar_b200_pass_multi)
+    CREATE_CUDA(cudaHostAlloc((void**)&c->h_out,
+                              (size_t)std::max(lay.size(true), 2 * lay.size(false)) * sizeof(double),
+                              cudaHostAllocDefault));
     CREATE_CUDA(cudaHostAlloc((void**)&c->h_f, 8 * (size_t)K * sizeof(double), cudaHostAllocDefault));
     CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CREATE_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));

@@ -709,6 +709,10 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allSta
     // two candidates per launch: second accumulator set -> at most 16 states per thread, hence K <= 1024, and the
     // e0 = exp(-u') sharing needs the multiplicative constant; the caller falls back to two launches otherwise
     if (M == 2 && (!(mode & 2) || K > 1024 || K < 2 || allStates || wantW)) return MBAR_B200_OK;
+    // Above 128 states the second accumulator set forces clusters of CTAs with 16 states per thread, and the
+    // per-tile cluster barrier then outweighs the shared exp (measured at K = 256: 8.0 ms vs 2 x 3.5 ms for two
+    // plain launches): the batched kernel is the default only where one CTA holds all states.
+    if (M == 2 && K > 128 && !std::getenv("MBAR_B200_M2_CLUSTERS")) return MBAR_B200_OK;
     const int cw = 8;
     const int rmax = (M == 2) ? 16 : 32;
     const int perCta = cw * rmax;                          // states one CTA can hold
@@ -740,6 +744,13 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allSta
     }
     const size_t header = fused_smem_header(K, p.CL, M);
     int ns = (int)((225 * 1024 - header - 16384) / p.stageBytes);   // (CL >= 4 -> 2 stages of 64 KB)
+    while (ns < 2 && p.TPW > 1) {
+        // (M = 2 with 8-CTA clusters: two sets of 64 exchange slots leave room for single-tile stages only)
+        const uint32_t pad = p.stageBytes - (uint32_t)p.Wn * p.TPW * ctaTileBytes;
+        p.TPW /= 2;
+        p.stageBytes = (((uint32_t)p.Wn * p.TPW * ctaTileBytes + pad) + 127u) & ~127u;
+        ns = (int)((225 * 1024 - header - 16384) / p.stageBytes);
+    }
     p.NS = ns > 8 ? 8 : ns;
     if (p.NS < 2) return MBAR_B200_OK;
     const int tilesPerStage = p.Wn * p.TPW;

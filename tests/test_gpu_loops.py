@@ -241,12 +241,23 @@ def test_hessian_beyond_2048_states(lib):
 def test_candidate_batched_pass_kernel(lib, K):
     """pass_fused_kernel<..., M = 2>: two candidate vectors on the same staged tile (single CTA up to K = 128,
     clusters of 2 / 4 / 8 CTAs above), against two single-candidate launches and the oracle."""
+    import os
+
     empty = () if K < 5 else (2,)
     u, N_k, f = _random_problem(K, (40 if K < 300 else 6) * K, seed=500 + K, empty=empty)
     s = N_k > 0
     rng = np.random.RandomState(K)
     f2 = np.stack([f, f + rng.normal(scale=0.3, size=K)])
     f2[:, ~s] = 0.0
+    # (above 128 states the batched kernel needs clusters and is not the default: switch it on for the test)
+    os.environ["MBAR_B200_M2_CLUSTERS"] = "1"
+    try:
+        _run_m2_case(lib, u, N_k, f2, s, rng)
+    finally:
+        del os.environ["MBAR_B200_M2_CLUSTERS"]
+
+
+def _run_m2_case(lib, u, N_k, f2, s, rng):
     with lib.DeviceProblem(u, N_k) as p:
         S, sumL = p.pass_multi(f2)
         assert "M=2" in p.last_kernels()["pass_kernel"], p.last_kernels()
