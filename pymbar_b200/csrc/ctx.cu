@@ -12,6 +12,8 @@
 #include <cstring>
 #include <algorithm>
 #include <cstdlib>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 
@@ -32,6 +34,84 @@ static thread_local char g_err[512] = "";
 // allocated the thread prefers the GPU's own node (sysfs numa_node of its PCI function); hosts without
 // NUMA information (-1) are left alone.  Raw syscalls: libnuma is not part of the image.
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// host worker pool (see internal.cuh)
+// ------------------------------------------------------------------------------------------
+namespace {
+struct HostPool {
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable cvStart, cvDone;
+    const std::function<void(int)>* fn = nullptr;
+    int nTasks = 0, next = 0, running = 0;
+    uint64_t generation = 0;
+    bool stop = false;
+    int width = 1;
+
+    HostPool() {
+        int hw = (int)std::thread::hardware_concurrency();
+        width = std::max(1, std::min(16, hw));
+        if (const char* v = std::getenv("MBAR_B200_HOST_THREADS")) width = std::max(1, std::min(64, std::atoi(v)));
+        for (int t = 1; t < width; ++t) workers.emplace_back([this] { loop(); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> g(m);
+            stop = true;
+        }
+        cvStart.notify_all();
+        for (auto& w : workers) w.join();
+    }
+    void drain(std::unique_lock<std::mutex>& lk) {
+        while (next < nTasks) {
+            const int i = next++;
+            ++running;
+            lk.unlock();
+            (*fn)(i);
+            lk.lock();
+            --running;
+        }
+    }
+    void loop() {
+        std::unique_lock<std::mutex> lk(m);
+        uint64_t seen = 0;
+        for (;;) {
+            cvStart.wait(lk, [&] { return stop || generation != seen; });
+            if (stop) return;
+            seen = generation;
+            drain(lk);
+            if (running == 0 && next >= nTasks) cvDone.notify_all();
+        }
+    }
+    void run(int n, const std::function<void(int)>& f) {
+        std::unique_lock<std::mutex> lk(m);
+        fn = &f;
+        nTasks = n;
+        next = 0;
+        ++generation;
+        cvStart.notify_all();
+        drain(lk);
+        cvDone.wait(lk, [&] { return running == 0 && next >= nTasks; });
+        fn = nullptr;
+    }
+};
+HostPool& pool() {
+    static HostPool p;
+    return p;
+}
+std::mutex g_poolUse;      // one parallel region at a time
+}  // namespace
+
+void host_parallel(int nTasks, const std::function<void(int)>& fn) {
+    if (nTasks <= 1) {
+        for (int i = 0; i < nTasks; ++i) fn(i);
+        return;
+    }
+    std::lock_guard<std::mutex> g(g_poolUse);
+    pool().run(nTasks, fn);
+}
+int host_parallel_width() { return pool().width; }
+
 int gpu_numa_node(int device) {
     static int cache[16] = {-2, -2, -2, -2, -2, -2, -2, -2, -2, -2, -2, -2, -2, -2, -2, -2};
     int& c = cache[device & 15];
@@ -455,24 +535,11 @@ int mbar_b200_host_hash(const void* base, int64_t rows, int64_t row_bytes, int64
     const int64_t perRow = row_bytes ? (row_bytes + blk - 1) / blk : 0;
     const int64_t nBlocks = rows * perRow;
     std::vector<uint64_t> part((size_t)nBlocks);
-    int nthr = (int)std::min<int64_t>(16, std::max<int64_t>(1, nBlocks));
-    const int hw = (int)std::thread::hardware_concurrency();
-    if (hw > 0 && nthr > hw) nthr = hw;
-    auto work = [&](int t) {
-        for (int64_t i = t; i < nBlocks; i += nthr) {
-            const int64_t r = i / perRow, c = i % perRow;
-            const int64_t off = c * blk, len = std::min(blk, row_bytes - off);
-            part[(size_t)i] = hash_span(b + r * stride_bytes + off, (size_t)len, 0x243F6A8885A308D3ull + (uint64_t)i);
-        }
-    };
-    if (nthr == 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> th;
-        for (int t = 1; t < nthr; ++t) th.emplace_back(work, t);
-        work(0);
-        for (auto& x : th) x.join();
-    }
+    host_parallel((int)std::min<int64_t>(nBlocks, 1 << 30), [&](int i) {
+        const int64_t r = i / perRow, c = i % perRow;
+        const int64_t off = c * blk, len = std::min(blk, row_bytes - off);
+        part[(size_t)i] = hash_span(b + r * stride_bytes + off, (size_t)len, 0x243F6A8885A308D3ull + (uint64_t)i);
+    });
     uint64_t h = 0x13198A2E03707344ull ^ (uint64_t)rows ^ ((uint64_t)row_bytes << 20);
     for (uint64_t v : part) h = mix64(h, v);
     *out = h;
@@ -801,18 +868,18 @@ int mbar_b200_upload_u_kn(mbar_b200_ctx* c, const double* u_host, int64_t ld) {
             MBAR_CUDA(cudaEventSynchronize(c->evCopy[buf]));
             // (numpy arrays are pageable: pack with several threads so the packing keeps up with PCIe)
             double* p = c->stage_pinned[buf];
-            const int nthr = std::max(1, std::min({8, K, (int)std::thread::hardware_concurrency()}));
-            auto pack = [&](int t) {
-                for (int k = t; k < K; k += nthr)
+            if ((size_t)w * K < (1u << 16)) {
+                for (int k = 0; k < K; ++k)
                     std::memcpy(p + (size_t)k * w, u_host + (size_t)k * ld + n0, (size_t)w * sizeof(double));
-            };
-            if (nthr == 1 || (size_t)w * K < (1u << 16)) {
-                for (int t = 0; t < nthr; ++t) pack(t);
             } else {
-                std::vector<std::thread> th;
-                for (int t = 1; t < nthr; ++t) th.emplace_back(pack, t);
-                pack(0);
-                for (auto& x : th) x.join();
+                // row segments in pieces of <= 128 KB so that small K still spreads over the pool
+                const int64_t piece = 16384;
+                const int64_t perRow = (w + piece - 1) / piece;
+                host_parallel((int)(K * perRow), [&](int task) {
+                    const int64_t k = task / perRow, c0 = (task % perRow) * piece;
+                    const int64_t len = std::min(piece, w - c0);
+                    std::memcpy(p + (size_t)k * w + c0, u_host + (size_t)k * ld + n0 + c0, (size_t)len * sizeof(double));
+                });
             }
             src = p;
             srcLd = w;

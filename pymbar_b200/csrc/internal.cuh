@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <functional>
 #include <vector>
 
 #include "../../include/mbar_b200.h"
@@ -215,6 +216,12 @@ struct NvtxRange {
     explicit NvtxRange(const char* name);
     ~NvtxRange();
 };
+
+// Persistent host worker threads for the memcpy-bound staging steps (packing pageable uploads, draining log W):
+// spawning threads per 64 MB chunk cost as much as a quarter of the chunk's copy time.  run(n, fn) executes
+// fn(0..n-1) on the pool plus the calling thread and returns when all are done.
+void host_parallel(int nTasks, const std::function<void(int)>& fn);
+int host_parallel_width();
 
 // Prefer the GPU's NUMA node for host allocations made while this object lives (ctx.cu).
 int gpu_numa_node(int device);

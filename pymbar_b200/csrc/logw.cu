@@ -1,6 +1,8 @@
 // mbar_log_W_nk / mbar_W_nk (mbar_solvers.py:439-507): logW[n, k] = f_k - u_kn - L_n, [N, K] row-major.
 // Reads the tile-major u' once (+ the stored L'_n) and writes the transposed [N, K] layout through a
 // 32 x 33 shared-memory transposition buffer per warp, so both the read and the write are coalesced.
+#include <sys/mman.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -60,6 +62,14 @@ int launch_logw(mbar_b200_ctx* ctx, const double* h_f, double* logW_host, int64_
         pinnedDst = (attr.type == cudaMemoryTypeHost);
     else
         cudaGetLastError();
+#if defined(MADV_HUGEPAGE)
+    if (!pinnedDst) {
+        // a freshly allocated destination is faulted in page by page while it is filled: ask for huge pages
+        const uintptr_t a0 = (reinterpret_cast<uintptr_t>(logW_host) + 4095) & ~(uintptr_t)4095;
+        const uintptr_t a1 = (reinterpret_cast<uintptr_t>(logW_host + (n - 1) * ld + K)) & ~(uintptr_t)4095;
+        if (a1 > a0 + (8u << 20)) madvise(reinterpret_cast<void*>(a0), a1 - a0, MADV_HUGEPAGE);
+    }
+#endif
     const int64_t tileFirst = n0 / TILE_N;
     const int64_t tilesTotal = (n + TILE_N - 1) / TILE_N;
     int64_t tilesPerChunk = (64ll << 20) / ((int64_t)K * TILE_N * 8);
@@ -86,23 +96,16 @@ int launch_logw(mbar_b200_ctx* ctx, const double* h_f, double* logW_host, int64_
         const int64_t rows = pend[b].rows;
         double* dst = logW_host + (pend[b].row0 - n0) * ld;
         const double* src = h_stage[b];
-        const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({8, rows, (int64_t)std::thread::hardware_concurrency()}));
-        auto work = [&](int t) {
-            const int64_t r0 = rows * t / nthr, r1 = rows * (t + 1) / nthr;
+        const int64_t rowsPer = std::max<int64_t>(1, (128 * 1024) / ((int64_t)K * 8));     // ~128 KB per task
+        const int nTasks = (int)((rows + rowsPer - 1) / rowsPer);
+        host_parallel(nTasks, [&](int t) {
+            const int64_t r0 = (int64_t)t * rowsPer, r1 = std::min(rows, r0 + rowsPer);
             if (ld == K) {
                 std::memcpy(dst + r0 * K, src + r0 * K, (size_t)(r1 - r0) * K * sizeof(double));
             } else {
                 for (int64_t r = r0; r < r1; ++r) std::memcpy(dst + r * ld, src + r * K, (size_t)K * sizeof(double));
             }
-        };
-        if (nthr == 1 || (size_t)rows * K < (1u << 16)) {
-            for (int t = 0; t < nthr; ++t) work(t);
-        } else {
-            std::vector<std::thread> th;
-            for (int t = 1; t < nthr; ++t) th.emplace_back(work, t);
-            work(0);
-            for (auto& x : th) x.join();
-        }
+        });
         pend[b].live = false;
     };
     int buf = 0;
