@@ -786,6 +786,15 @@ int mbar_b200_get_counters(const mbar_b200_ctx* c, int64_t* launches, int64_t* p
 
 int mbar_b200_last_pass_ms(mbar_b200_ctx* c, double* ms) {
     MBAR_REQUIRE(c && ms, MBAR_B200_ERR_INVALID, "NULL argument");
+    // events recorded around the most recent pass-kernel launch on the context's stream (whichever entry point
+    // launched it)
+    cudaSetDevice(c->device);
+    float t = 0.f;
+    if (c->stream && cudaStreamSynchronize(c->stream) == cudaSuccess &&
+        cudaEventElapsedTime(&t, c->evA, c->evB) == cudaSuccess)
+        c->lastPassMs = t;
+    else
+        cudaGetLastError();
     *ms = c->lastPassMs;
     return MBAR_B200_OK;
 }
