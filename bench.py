@@ -542,7 +542,8 @@ def e2e_legs(rig, args, prob, K, N_local, N_k):
     ms._DEVICE = rig.local
     pin = PinnedArray((K, N_local))
     prob.download(0, N_local, out=pin.array)           # setup: host copy of this rank's shard
-    prob.close()                                       # never two 20 GB problems + staging at once
+    if not rig.distributed:
+        prob.close()                                   # never two 20 GB problems + staging at once
     h2d0 = 8 * K * N_local + 8 * K
     res = {}
     for kind in ("pinned", "pageable"):
@@ -560,7 +561,13 @@ def e2e_legs(rig, args, prob, K, N_local, N_k):
         for i in range(1 + nsteps):
             rig.barrier()
             t0 = time.perf_counter()
-            out = ms.self_consistent_update(src, N_k, fh)
+            if rig.distributed:
+                # ONE sample-sharded call: every rank re-uploads its host shard into the attached problem, the
+                # pass runs on all GPUs and the partial sums are all-reduced (NCCL) before f comes back
+                prob.upload(src)
+                out = prob.self_consistent_update(fh)
+            else:
+                out = ms.self_consistent_update(src, N_k, fh)
             dt = time.perf_counter() - t0
             if i > 0:
                 times.append(dt)
@@ -571,11 +578,22 @@ def e2e_legs(rig, args, prob, K, N_local, N_k):
                      "h2d_gbs": h2d0 / e2e_s / 1e9, "pcie_fraction_of_gen5_x16": h2d0 / e2e_s / 63.0e9}
         if kind == "pageable":
             del src
+    if rig.distributed:
+        # every rank must hold the same f after the sharded call
+        same = [None] * rig.world
+        rig.dist.all_gather_object(same, fh.tobytes())
+        res["pinned"]["bit_identical_f_across_ranks"] = all(b == same[0] for b in same)
+        prob.close()
     e2e = dict(res["pinned"])
-    e2e["call"] = ("pymbar_b200.mbar_solvers.self_consistent_update(u_kn_host[pinned], N_k, f_k), "
-                   "PYMBAR_B200_CACHE=0 (create + upload + pass + destroy per call)")
-    e2e["note"] = ("each rank runs the call on its own shard; time = max over ranks (the data path has no "
-                   "collective in this leg)") if rig.distributed else "single GPU"
+    if rig.distributed:
+        e2e["call"] = ("DeviceProblem.upload(u_kn_host_shard[pinned]) + DeviceProblem.self_consistent_update(f_k) on "
+                       "the sample-sharded problem of all ranks (upload of every shard + pass + NCCL all-reduce of "
+                       "the partial sums inside every step)")
+        e2e["note"] = "one multi-GPU call per step; time = max over ranks"
+    else:
+        e2e["call"] = ("pymbar_b200.mbar_solvers.self_consistent_update(u_kn_host[pinned], N_k, f_k), "
+                       "PYMBAR_B200_CACHE=0 (create + upload + pass + destroy per call)")
+        e2e["note"] = "single GPU"
     e2e["pageable_source"] = res.get("pageable")
     e2e["pcie_note"] = "fraction of 63 GB/s (PCIe Gen5 x16 payload ceiling); the step is the 20.48 GB upload"
     try:
