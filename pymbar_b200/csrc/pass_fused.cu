@@ -737,7 +737,7 @@ int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allSta
     {
         // the masked variants read (and discard) up to R rows per warp regardless of how many it owns:
         // pad every ring slot so that those reads never touch a slot the TMA engine may be filling
-        const int rt = p.Rw <= 8 ? 8 : p.Rw <= 16 ? 16 : 32;
+        const int rt = p.Rw <= 8 ? 8 : p.Rw <= 16 ? 16 : p.Rw <= 24 ? 24 : 32;
         const int over = (p.Wk - 1) * p.Rw + rt - p.Kh;          // rows past the CTA's last state
         if (over > 0) p.stageBytes += (uint32_t)over * TILE_N * 8;
         p.stageBytes = (p.stageBytes + 127u) & ~127u;
@@ -788,7 +788,9 @@ int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
     const size_t smem = fused_smem_header(p.K, p.CL, p.M) + (size_t)p.NS * p.stageBytes + 16384;
     int64_t grid = p.nStages < ctx->smCount / p.CL ? p.nStages : ctx->smCount / p.CL;
     grid *= p.CL;
-    const int Rt = p.Rw <= 8 ? 8 : p.Rw <= 16 ? 16 : 32;
+    // register rows per thread: 8 / 16 / 24 / 32 (24 keeps K = 96, 192, 384, 768, 1536 and their neighbours on
+    // the unmasked family: 8 warps x 24 states instead of 32 register rows of which a quarter is discarded)
+    const int Rt = p.Rw <= 8 ? 8 : p.Rw <= 16 ? 16 : (p.Rw <= 24 && p.M == 1) ? 24 : 32;
     const bool full = (p.Rw == Rt) && (p.K == p.CL * p.Wk * p.Rw) &&
                       ((int)ctx->active.size() == p.K || p.allStates) && !p.wgt;
     void (*kern)(const FusedParams) = nullptr;
@@ -817,22 +819,24 @@ int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
         PICKM(8, 1, 40) PICKM(16, 1, 42) PICKM(16, 2, 44) PICKM(16, 4, 46) PICKM(16, 8, 48)
     } else {
         PICK(8, 1, 0) PICK(16, 1, 4) PICK(32, 1, 8) PICK(32, 2, 12) PICK(32, 4, 16) PICK(32, 8, 20)
+        PICK(24, 1, 60) PICK(24, 2, 64) PICK(24, 4, 68) PICK(24, 8, 72)
         PICKW(32, 1, 24) PICKW(32, 2, 28) PICKW(32, 4, 32) PICKW(32, 8, 36) PICKW(16, 1, 52) PICKW(8, 1, 56)
+        PICKW(24, 1, 76) PICKW(24, 2, 80) PICKW(24, 4, 84) PICKW(24, 8, 88)
     }
 #undef PICKM
 #undef PICKW
 #undef PICK
     MBAR_REQUIRE(kern, MBAR_B200_ERR_INVALID, "no fused kernel variant for K=%d", p.K);
-    MBAR_REQUIRE(!p.Wout || (which >= 24 && which < 40) || which >= 52, MBAR_B200_ERR_INVALID,
-                 "no weight-storing fused variant for K=%d", p.K);
+    const bool isW = (which >= 24 && which < 40) || (which >= 52 && which < 60) || which >= 76;
+    MBAR_REQUIRE(!p.Wout || isW, MBAR_B200_ERR_INVALID, "no weight-storing fused variant for K=%d", p.K);
     snprintf(ctx->lastKernel, sizeof(ctx->lastKernel),
              "pass_fused_kernel<R=%d, %s, CW=8, BATCH=8, MODE=%d (%s), CL=%d%s> grid=%lld NS=%d TPW=%d", Rt,
              full ? "FULL" : "MASKED", (p.mode & 2) ? 3 : 1,
              (p.mode & 2) ? "LDS table + multiplicative state constant" : "LDS table", p.CL,
              (which >= 40 && which < 52) ? ", M=2 (two candidates per launch)"
-                           : (which >= 24) ? ", WST (weights stored for the Hessian)" : "",
+                           : isW ? ", WST (weights stored for the Hessian)" : "",
              (long long)grid, p.NS, p.TPW);
-    static size_t attrSetAll[16][60] = {{0}};          // per device: the attribute belongs to the context
+    static size_t attrSetAll[16][96] = {{0}};          // per device: the attribute belongs to the context
     size_t* attrSet = attrSetAll[ctx->device & 15];
     if (attrSet[which] < smem) {
         MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -275,3 +275,27 @@ def _run_m2_case(lib, u, N_k, f2, s, rng):
         S1, sumL1, _ = p.streaming_pass(f2[1])
         np.testing.assert_allclose(Sw[1], S1, rtol=1e-12, atol=1e-300)
         np.testing.assert_allclose(sumLw[1], sumL1, rtol=1e-13)
+
+
+@pytest.mark.parametrize("K", [24, 48, 96, 192, 384, 768])
+def test_24_row_kernel_family(lib, K):
+    """K = 8 warps x 24 states (x CTAs of a cluster): the R = 24 family of the fused pass, unmasked when every
+    state is sampled, masked otherwise; pass, weights for the Hessian and device loop against the oracle."""
+    for empty in ((), (3,)):
+        u, N_k, f = _random_problem(K, (30 if K < 300 else 8) * K, seed=900 + K, empty=empty)
+        s = N_k > 0
+        with lib.DeviceProblem(u, N_k) as p:
+            S, sumL, _ = p.streaming_pass(f)
+            assert "R=24" in p.last_kernels()["pass_kernel"], p.last_kernels()
+            assert ("FULL" in p.last_kernels()["pass_kernel"]) == (len(empty) == 0)
+            S_ref, L_ref = orc.single_pass_sums(u[s], N_k[s], f[s])
+            np.testing.assert_allclose(S[s], S_ref, rtol=1e-11)
+            np.testing.assert_allclose(sumL, L_ref.sum(), rtol=1e-12)
+            H = p.hessian(f)
+            np.testing.assert_allclose(H[np.ix_(s, s)], orc.mbar_hessian(u[s], N_k[s], f[s]), rtol=1e-9,
+                                       atol=1e-11 * N_k.max())
+            if K <= 192:
+                fk, r = p.solve_adaptive(np.zeros(K), tol=1e-12, min_sc_iter=0)
+                assert r["success"]
+                g = orc.mbar_gradient(u[s], N_k[s], fk[s])
+                assert np.max(np.abs(g)) < 1e-7 * N_k.max()
