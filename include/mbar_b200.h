@@ -192,6 +192,9 @@ int mbar_b200_solve_adaptive(mbar_b200_ctx* ctx, double* f_inout, double tol, in
 int mbar_b200_set_loop_mode(mbar_b200_ctx* ctx, int32_t mode, int32_t batch);
 /* Host synchronisations spent polling the device-resident loops since creation, current mode and batch. */
 int mbar_b200_get_loop_stats(const mbar_b200_ctx* ctx, int64_t* polls, int32_t* mode, int32_t* batch);
+/* The adaptive iteration is captured into a CUDA graph after the first batch a context runs and relaunched once
+ * per iteration: how often it was captured / launched (MBAR_B200_NO_GRAPH=1 disables the capture). */
+int mbar_b200_get_graph_stats(const mbar_b200_ctx* ctx, int64_t* captures, int64_t* launches);
 /* Run exactly `iters` self-consistent passes back to back with no host round trip (bench). */
 int mbar_b200_sci_iterate(mbar_b200_ctx* ctx, double* f_inout, int32_t iters);
 

@@ -74,6 +74,7 @@ SIGNATURES = {
                                            C.POINTER(SolveResult)]),
     "mbar_b200_set_loop_mode": (C.c_int, [_ctx, C.c_int32, C.c_int32]),
     "mbar_b200_get_loop_stats": (C.c_int, [_ctx, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "mbar_b200_get_graph_stats": (C.c_int, [_ctx, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mbar_b200_last_kernels": (C.c_int, [_ctx, C.c_char_p, C.c_char_p, C.c_int32]),
     "mbar_b200_last_hessian_ms": (C.c_int, [_ctx, _dp, _dp]),
     "mbar_b200_measure_fp64_peak": (C.c_int, [C.c_int, _dp, _dp]),

@@ -389,6 +389,13 @@ int mbar_b200_get_loop_stats(const mbar_b200_ctx* c, int64_t* polls, int32_t* mo
     return MBAR_B200_OK;
 }
 
+int mbar_b200_get_graph_stats(const mbar_b200_ctx* c, int64_t* captures, int64_t* launches) {
+    MBAR_REQUIRE(c, MBAR_B200_ERR_INVALID, "ctx is NULL");
+    if (captures) *captures = c->graphCaptures;
+    if (launches) *launches = c->graphLaunches;
+    return MBAR_B200_OK;
+}
+
 int mbar_b200_self_consistent_update(mbar_b200_ctx* c, const double* f, double* f_out) {
     MBAR_REQUIRE(f_out, MBAR_B200_ERR_INVALID, "f_out is NULL");
     PassWant w;

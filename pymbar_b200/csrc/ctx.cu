@@ -715,6 +715,7 @@ int mbar_b200_destroy(mbar_b200_ctx* c) {
     cudaFree(c->d_scratch);
     cudaFree(c->d_loop); cudaFree(c->d_av); cudaFree(c->d_outM); cudaFree(c->d_A); cudaFree(c->d_active);
     cudaFree(c->d_seq); cudaFree(c->d_Wt);
+    if (c->loopGraph) cudaGraphExecDestroy(c->loopGraph);
     if (c->h_loop) cudaFreeHost(c->h_loop);
     if (c->evH0) cudaEventDestroy(c->evH0);
     if (c->evH1) cudaEventDestroy(c->evH1);

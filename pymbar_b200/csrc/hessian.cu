@@ -613,7 +613,7 @@ int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, Loo
     const PassLayout lay{K};
     const unsigned long long* mask = allRows ? ctx->d_onesmask : ctx->d_rowmask;
     static const bool forceOld = std::getenv("MBAR_B200_HESSIAN_INPLACE") != nullptr;
-    MBAR_CUDA(cudaEventRecord(ctx->evH0, ctx->stream));
+    if (!ctx->capturing) MBAR_CUDA(cudaEventRecord(ctx->evH0, ctx->stream));
     if (K <= 64 && !forceOld) {
         const int KT = K <= 16 ? 2 : K <= 32 ? 4 : 8;
         const int KP = KT * 8;
@@ -638,14 +638,14 @@ int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, Loo
             MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             a = smem;
         }
-        MBAR_CUDA(cudaEventRecord(ctx->evH1, ctx->stream));
+        if (!ctx->capturing) MBAR_CUDA(cudaEventRecord(ctx->evH1, ctx->stream));
         kern<<<(unsigned)grid, 256, smem, ctx->stream>>>(win ? ctx->d_Wt : ctx->d_u, ctx->d_L, d_ch, mask, K, ctx->N,
                                                         ctx->nTiles, nslot, ctx->d_W, ctx->d_sqrtw, loop);
         MBAR_CUDA(cudaGetLastError());
         hessian_small_reduce_kernel<<<(KP * KP + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_W, K, KP, (int)grid,
                                                                                     ctx->d_out + lay.G(), loop);
         MBAR_CUDA(cudaGetLastError());
-        MBAR_CUDA(cudaEventRecord(ctx->evH2, ctx->stream));
+        if (!ctx->capturing) MBAR_CUDA(cudaEventRecord(ctx->evH2, ctx->stream));
         snprintf(ctx->lastHessKernel, sizeof(ctx->lastHessKernel), "hessian_small_kernel<KT=%d, %s> grid=%lld NSLOT=%d",
                  KT, win ? "weights stored by the fused pass (WST)" : "in-register conversion", (long long)grid, nslot);
         ctx->launches += 2;
@@ -671,7 +671,7 @@ int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, Loo
         MBAR_CUDA(cudaGetLastError());
         ctx->launches++;
     }
-    MBAR_CUDA(cudaEventRecord(ctx->evH1, ctx->stream));
+    if (!ctx->capturing) MBAR_CUDA(cudaEventRecord(ctx->evH1, ctx->stream));
     // pairs in launches of at most 128 (K <= 2048: one launch; the split table is a kernel parameter)
     int totalCtas = 0;
     for (int base = 0; base < nPairsAll; base += 128) {
@@ -751,7 +751,7 @@ int launch_hessian_dev(mbar_b200_ctx* ctx, const double* d_ch, bool allRows, Loo
                  totalCtas);
     else
         snprintf(ctx->lastHessKernel, sizeof(ctx->lastHessKernel), "hessian_inplace_kernel (round 1), CTAs %d", totalCtas);
-    MBAR_CUDA(cudaEventRecord(ctx->evH2, ctx->stream));
+    if (!ctx->capturing) MBAR_CUDA(cudaEventRecord(ctx->evH2, ctx->stream));
     ctx->passes++;
     return MBAR_B200_OK;
 }

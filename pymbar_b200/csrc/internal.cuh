@@ -157,6 +157,12 @@ struct mbar_b200_ctx {
     int loopMode = 0;                    // 0 device-resident, 1 host-stepped (round-1 behaviour)
     int loopBatch = 4;                   // iterations enqueued between two polls of LoopState
     int64_t loopPolls = 0;               // host synchronisations spent polling LoopState
+    // the adaptive iteration as a CUDA graph (captured once, relaunched per iteration; see loops.cu)
+    bool capturing = false;              // stream capture in progress: no timing events, no allocations
+    bool graphWarm = false;              // one uncaptured iteration has sized every buffer / kernel attribute
+    cudaGraphExec_t loopGraph = nullptr;
+    std::vector<uint64_t> loopGraphKey;
+    int64_t graphLaunches = 0, graphCaptures = 0;
     double* d_Wt = nullptr;              // [nTiles][K][32] materialised N_k W_nk (swizzled) for the Hessian
     bool wtAllocFailed = false;
     size_t gpartBytes = 0;               // size of d_W (per-CTA partial blocks of the Hessian kernels)
@@ -251,7 +257,8 @@ int launch_pass_fused(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool al
 // d_cdst / h_stage: where c = f + log N - mid is staged (default: ctx->d_c / ctx->h_f); midForce: reuse the
 // centring of a previous prepare (candidates evaluated against the same exp(c) range), NaN = derive from f
 int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, FusedParams* out, bool* ok,
-                  double* d_cdst = nullptr, double* h_stage = nullptr, bool wantW = false, int M = 1);
+                  double* d_cdst = nullptr, double* h_stage = nullptr, bool wantW = false, int M = 1,
+                  double midQuantum = 0.0);
 int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p);
 bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, bool allStates, double* midOut, double* spreadOut);
 // weightsReady: the fused pass at this f already wrote N_k W_nk into ctx->d_Wt (FusedParams::Wout)

@@ -566,6 +566,77 @@ static int enqueue_adaptive_iteration(mbar_b200_ctx* c, const FusedParams& pF, c
     return MBAR_B200_OK;
 }
 
+// Everything that distinguishes two launches of the fused kernel (the captured graph bakes these in).
+static void key_push(std::vector<uint64_t>& key, const FusedParams& p) {
+    auto bits = [](double v) { uint64_t u; std::memcpy(&u, &v, 8); return u; };
+    const uint64_t f[] = {(uint64_t)(uintptr_t)p.u, (uint64_t)(uintptr_t)p.c, (uint64_t)(uintptr_t)p.c2,
+                          (uint64_t)(uintptr_t)p.out, (uint64_t)(uintptr_t)p.out2, (uint64_t)(uintptr_t)p.Lout,
+                          (uint64_t)(uintptr_t)p.Wout, (uint64_t)(uintptr_t)p.wgt, (uint64_t)(uintptr_t)p.loop,
+                          (uint64_t)(uintptr_t)p.rowmask, (uint64_t)(uintptr_t)p.Nk, (uint64_t)(uintptr_t)p.peer.seq,
+                          bits(p.mid), bits(p.mid2), bits(p.sumW), (uint64_t)p.N, (uint64_t)p.nStages,
+                          (uint64_t)p.K | ((uint64_t)p.CL << 16) | ((uint64_t)p.M << 24) | ((uint64_t)p.mode << 28) |
+                              ((uint64_t)p.NS << 32) | ((uint64_t)p.TPW << 40) | ((uint64_t)p.Wk << 48) | ((uint64_t)p.Rw << 56),
+                          (uint64_t)p.peer.nranks | ((uint64_t)p.peer.rank << 8) | ((uint64_t)p.epi << 16) |
+                              ((uint64_t)p.first << 24) | ((uint64_t)p.debugSkip << 56)};
+    key.insert(key.end(), f, f + sizeof(f) / sizeof(f[0]));
+}
+
+// `batch` adaptive iterations.  The first batch a context ever runs is enqueued kernel by kernel (it sizes the
+// buffers and sets the kernel attributes); after that ONE iteration is captured into a CUDA graph and relaunched:
+// an iteration is ~11 launches and ~9 event records, which at C2 / C4 sizes (30-150 us kernels) cost as much
+// as a third of the iteration when enqueued one by one.  The graph is kept across batches and across solves as
+// long as the launch parameters are the same (the centring constant is quantised for that purpose).
+static int run_adaptive_batch(mbar_b200_ctx* c, const FusedParams& pF, const FusedParams& pS, const FusedParams& pN,
+                              const FusedParams* pM, int batch) {
+    static const bool noGraph = std::getenv("MBAR_B200_NO_GRAPH") != nullptr;
+    if (noGraph || !c->graphWarm) {
+        for (int b = 0; b < batch; ++b) MBAR_TRY(enqueue_adaptive_iteration(c, pF, pS, pN, pM));
+        c->graphWarm = true;
+        return MBAR_B200_OK;
+    }
+    std::vector<uint64_t> key;
+    key_push(key, pF);
+    key_push(key, pS);
+    key_push(key, pN);
+    if (pM) key_push(key, *pM);
+    key.push_back((uint64_t)c->nranks | ((uint64_t)c->peerReady << 8) | ((uint64_t)(uintptr_t)c->comm << 16));
+    if (!c->loopGraph || key != c->loopGraphKey) {
+        if (c->loopGraph) {
+            cudaGraphExecDestroy(c->loopGraph);
+            c->loopGraph = nullptr;
+        }
+        const int64_t launches0 = c->launches, passes0 = c->passes;
+        c->capturing = true;
+        cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed);
+        int rc = MBAR_B200_OK;
+        if (e == cudaSuccess) rc = enqueue_adaptive_iteration(c, pF, pS, pN, pM);
+        cudaGraph_t g = nullptr;
+        if (e == cudaSuccess) e = cudaStreamEndCapture(c->stream, &g);
+        c->capturing = false;
+        c->launches = launches0;
+        c->passes = passes0;
+        if (e == cudaSuccess && rc == MBAR_B200_OK && g) e = cudaGraphInstantiate(&c->loopGraph, g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (e != cudaSuccess || rc != MBAR_B200_OK || !c->loopGraph) {
+            // capture is an optimisation: fall back to plain launches for this batch
+            cudaGetLastError();
+            c->loopGraph = nullptr;
+            c->loopGraphKey.clear();
+            for (int b = 0; b < batch; ++b) MBAR_TRY(enqueue_adaptive_iteration(c, pF, pS, pN, pM));
+            return MBAR_B200_OK;
+        }
+        c->loopGraphKey = key;
+        c->graphCaptures++;
+    }
+    for (int b = 0; b < batch; ++b) {
+        MBAR_CUDA(cudaGraphLaunch(c->loopGraph, c->stream));
+        c->graphLaunches++;
+        c->launches += 11;
+        c->passes += pM ? 3 : 4;
+    }
+    return MBAR_B200_OK;
+}
+
 int solve_adaptive_device(mbar_b200_ctx* c, double* f, double tol, int32_t maxiter, int32_t min_sc_iter,
                           double gamma, mbar_b200_solve_result* res) {
     MBAR_REQUIRE(c->ready, MBAR_B200_ERR_NOT_READY, "u_kn has not been uploaded");
@@ -593,7 +664,7 @@ int solve_adaptive_device(mbar_b200_ctx* c, double* f, double tol, int32_t maxit
         itersBefore = c->h_loop->iterations;
         FusedParams pF;
         bool ok = false;
-        MBAR_TRY(fused_prepare(c, cur.data(), true, false, &pF, &ok, nullptr, nullptr, true));
+        MBAR_TRY(fused_prepare(c, cur.data(), true, false, &pF, &ok, nullptr, nullptr, true, 1, 16.0));
         if (!ok) { fallback = true; break; }
         std::memcpy(c->h_f + 4 * K, cur.data(), K * sizeof(double));
         MBAR_CUDA(cudaMemcpyAsync(c->d_f, c->h_f + 4 * K, K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -615,7 +686,7 @@ int solve_adaptive_device(mbar_b200_ctx* c, double* f, double tol, int32_t maxit
         static const bool noM2 = std::getenv("MBAR_B200_NO_M2") != nullptr;
         if (!noM2)
             MBAR_TRY(fused_prepare(c, cur.data(), false, false, &pM, &okM, c->d_av + AV_CSCI * K, c->h_f + 6 * K,
-                                   false, 2));
+                                   false, 2, 16.0));
         if (okM) {
             pM.loop = c->d_loop;
             pM.first = g0;
@@ -626,8 +697,7 @@ int solve_adaptive_device(mbar_b200_ctx* c, double* f, double tol, int32_t maxit
             pM.out = pS.out;
             pM.out2 = pN.out;
         }
-        for (int b = 0; b < c->loopBatch; ++b)
-            MBAR_TRY(enqueue_adaptive_iteration(c, pF, pS, pN, okM ? &pM : nullptr));
+        MBAR_TRY(run_adaptive_batch(c, pF, pS, pN, okM ? &pM : nullptr, c->loopBatch));
         usedM2 = usedM2 || okM;
         MBAR_TRY(loop_poll(c));
         const LoopState& st = *c->h_loop;

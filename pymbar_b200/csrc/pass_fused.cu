@@ -689,12 +689,15 @@ bool fused_applicable(const mbar_b200_ctx* ctx, const double* h_f, bool allState
 
 // Configure the fused kernel for f (host) and stage c = f + log N - mid on the device.
 int fused_prepare(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool allStates, FusedParams* out,
-                  bool* ok, double* d_cdst, double* h_stage, bool wantW, int M) {
+                  bool* ok, double* d_cdst, double* h_stage, bool wantW, int M, double midQuantum) {
     if (!d_cdst) d_cdst = ctx->d_c;
     if (!h_stage) h_stage = ctx->h_f;
     *ok = false;
     double mid = 0.0, spread = 0.0;
     if (!fused_applicable(ctx, h_f, allStates, &mid, &spread)) return MBAR_B200_OK;
+    // (any centring within a few units of the midpoint is as good; a quantised one lets consecutive batches and
+    //  solves of the device-resident loops launch with identical parameters, i.e. reuse one captured graph)
+    if (midQuantum > 0.0) mid = midQuantum * std::nearbyint(mid / midQuantum);
     const int K = ctx->K;
     FusedParams p{};
     p.K = K;
@@ -842,7 +845,7 @@ int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
         MBAR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attrSet[which] = smem;
     }
-    MBAR_CUDA(cudaEventRecord(ctx->evA, ctx->stream));
+    if (!ctx->capturing) MBAR_CUDA(cudaEventRecord(ctx->evA, ctx->stream));
     if (p.CL == 1) {
         kern<<<(unsigned)grid, p.CW * 32, smem, ctx->stream>>>(p);
     } else {
@@ -860,7 +863,7 @@ int fused_enqueue(mbar_b200_ctx* ctx, const FusedParams& p) {
         cfg.numAttrs = 1;
         MBAR_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     }
-    MBAR_CUDA(cudaEventRecord(ctx->evB, ctx->stream));
+    if (!ctx->capturing) MBAR_CUDA(cudaEventRecord(ctx->evB, ctx->stream));
     ctx->launches++;
     ctx->passes++;
     MBAR_CUDA(cudaGetLastError());

@@ -323,7 +323,10 @@ class DeviceProblem:
     def loop_stats(self):
         polls, mode, batch = C.c_int64(0), C.c_int32(0), C.c_int32(0)
         check(self._lib.mbar_b200_get_loop_stats(self._h, C.byref(polls), C.byref(mode), C.byref(batch)))
-        return dict(polls=polls.value, mode="stepped" if mode.value else "device", batch=batch.value)
+        cap, lau = C.c_int64(0), C.c_int64(0)
+        check(self._lib.mbar_b200_get_graph_stats(self._h, C.byref(cap), C.byref(lau)))
+        return dict(polls=polls.value, mode="stepped" if mode.value else "device", batch=batch.value,
+                    graph_captures=cap.value, graph_launches=lau.value)
 
     def last_kernels(self):
         a, b = C.create_string_buffer(256), C.create_string_buffer(256)
