@@ -55,27 +55,52 @@ pass_generic_kernel(const double* __restrict__ u, int K, int64_t N, int64_t nTil
         const bool valid = tile * TILE_N + lane < N;
         const double wn = wgt ? __ldg(wgt + tile * TILE_N + lane) : 1.0;   // bootstrap multiplicity
         const double logwn = wgt ? log(wn) : 0.0;
+        // Sweeps 1 and 2 (per-sample max, then the shifted sum) with 8 rows in flight per thread: this kernel is
+        // bound by the bytes it keeps in flight, not by its arithmetic.  `c` carries -1e300 for rows that do not
+        // enter the denominator, so no mask is consulted here (exp(-1e300 - ...) is clamped to e^-800 = 0).
         double m = -INFINITY;
-        for (int k = 0; k < K; ++k)
-            if (row_active(rowmask, k)) m = fmax(m, __ldg(c + k) - tp[(int64_t)k * TILE_N]);
+        int k = 0;
+        for (; k + 8 <= K; k += 8) {
+            double v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = tp[(int64_t)(k + i) * TILE_N];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m = fmax(m, __ldg(c + k + i) - v[i]);
+        }
+        for (; k < K; ++k) m = fmax(m, __ldg(c + k) - tp[(int64_t)k * TILE_N]);
         double D = 0.0;
-        for (int k = 0; k < K; ++k)
-            if (row_active(rowmask, k))
-                D += exp_fast(fmax(__ldg(c + k) - tp[(int64_t)k * TILE_N] - m, -800.0), tab);
+        k = 0;
+        for (; k + 8 <= K; k += 8) {
+            double v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = tp[(int64_t)(k + i) * TILE_N];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) D += exp_fast(fmax(__ldg(c + k + i) - v[i] - m, -800.0), tab);
+        }
+        for (; k < K; ++k) D += exp_fast(fmax(__ldg(c + k) - tp[(int64_t)k * TILE_N] - m, -800.0), tab);
         const double Lp = m + log(D);
         if (Lout) Lout[tile * TILE_N + lane] = Lp;
         if (valid) sumL += wn * Lp;
         for (int k0 = 0; k0 < K; k0 += 32) {
             const int kmax = min(32, K - k0);
-            for (int kk = 0; kk < kmax; ++kk) {
-                const int k = k0 + kk;
-                const double uv = tp[(int64_t)k * TILE_N];
-                double val;
-                if (row_active(linmask, k))
-                    val = valid ? wn * exp_fast(fmax(__ldg(c + k) - uv - Lp, -800.0), tab) : 0.0;
-                else
-                    val = (kNeedUnsampled && valid) ? (__ldg(f + k) - uv - Lp + logwn) : -INFINITY;
-                T[kk * 33 + lane] = val;
+            for (int kb = 0; kb < kmax; kb += 8) {
+                double uv8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) uv8[i] = (kb + i < kmax) ? tp[(int64_t)(k0 + kb + i) * TILE_N] : 0.0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int kk = kb + i;
+                    if (kk < kmax) {
+                        const int k = k0 + kk;
+                        const double uv = uv8[i];
+                        double val;
+                        if (row_active(linmask, k))
+                            val = valid ? wn * exp_fast(fmax(__ldg(c + k) - uv - Lp, -800.0), tab) : 0.0;
+                        else
+                            val = (kNeedUnsampled && valid) ? (__ldg(f + k) - uv - Lp + logwn) : -INFINITY;
+                        T[kk * 33 + lane] = val;
+                    }
+                }
             }
             __syncwarp();
             const int k = k0 + lane;
@@ -191,7 +216,7 @@ int launch_pass_generic(mbar_b200_ctx* ctx, const double* h_f, bool wantL, bool 
     // c (sampled) and f (all) to the device
     for (int k = 0; k < K; ++k) {
         const double fk = h_f[k];
-        ctx->h_f[k] = std::isinf(ctx->h_logNk[k]) ? 0.0 : fk + ctx->h_logNk[k];
+        ctx->h_f[k] = std::isinf(ctx->h_logNk[k]) ? -1.0e300 : fk + ctx->h_logNk[k];   // (-1e300: not in the denominator)
         ctx->h_f[K + k] = fk;
     }
     MBAR_CUDA(cudaMemcpyAsync(ctx->d_c, ctx->h_f, 2 * (size_t)K * sizeof(double), cudaMemcpyHostToDevice,
