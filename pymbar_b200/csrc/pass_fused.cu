@@ -357,7 +357,44 @@ __global__ void __launch_bounds__(CW * 32, 1) pass_fused_kernel(const FusedParam
                     for (int r = 0; r < R; ++r) Dp2 = fma(lds_f64(c_s2 + k0 + r), e[r], Dp2);
                     D2 = Dp2;
                 }
-                if (CL > 1) {
+                if (CL >= 4) {
+                    // Two-level exchange (K > 512): the 8 warps of this CTA first combine their partial sums
+                    // locally (slots CL .. CL+7 of this parity, one named barrier), then ONE warp publishes the
+                    // CTA's sum to every partner through distributed shared memory and all CTAs add the CL
+                    // sums in rank order — 8x fewer remote stores and CL instead of 8 CL additions per thread
+                    // than the flat scheme used for pairs of CTAs.
+                    double* xb = xD + par * M * SLOTS * 32 + lane;
+                    xb[(CL + w) * 32] = Dp;
+                    if constexpr (M == 2) xb[(SLOTS + CL + w) * 32] = Dp2;
+                    named_bar_sync(1, CW * 32);
+                    if (w == 0) {
+                        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                        for (int ww = 0; ww < 8; ++ww) s1 += xb[(CL + ww) * 32];
+                        if constexpr (M == 2) {
+#pragma unroll
+                            for (int ww = 0; ww < 8; ++ww) s2 += xb[(SLOTS + CL + ww) * 32];
+                        }
+                        double* x = xb + half * 32;
+                        *x = s1;
+                        if constexpr (M == 2) x[SLOTS * 32] = s2;
+#pragma unroll
+                        for (int q = 1; q < CL; ++q) {
+                            st_cluster_f64(x, (unsigned)((half + q) % CL), s1);
+                            if constexpr (M == 2) st_cluster_f64(x + SLOTS * 32, (unsigned)((half + q) % CL), s2);
+                        }
+                    }
+                    cluster_barrier();
+                    D = 0.0;
+#pragma unroll
+                    for (int q = 0; q < CL; ++q) D += xb[q * 32];
+                    if constexpr (M == 2) {
+                        D2 = 0.0;
+#pragma unroll
+                        for (int q = 0; q < CL; ++q) D2 += xb[(SLOTS + q) * 32];
+                    }
+                    par ^= 1;
+                } else if (CL > 1) {
                     // CL*8 partial sums per sample: slot = owner rank * 8 + warp, written locally and into
                     // every partner CTA's shared memory; all CTAs then add them in the same order
                     double* x = xD + (par * M * SLOTS + half * 8 + w) * 32 + lane;
