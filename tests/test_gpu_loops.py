@@ -282,7 +282,10 @@ def test_24_row_kernel_family(lib, K):
     """K = 8 warps x 24 states (x CTAs of a cluster): the R = 24 family of the fused pass, unmasked when every
     state is sampled, masked otherwise; pass, weights for the Hessian and device loop against the oracle."""
     for empty in ((), (3,)):
-        u, N_k, f = _random_problem(K, (30 if K < 300 else 8) * K, seed=900 + K, empty=empty)
+        per = 30 if K < 300 else 8
+        u, N_k, f = _random_problem(K, per * K, seed=900 + K, empty=empty)
+        for e in empty:      # an unsampled state has no samples in the data set (sum N_k = N, as pymbar requires)
+            u = np.delete(u, np.s_[e * per:(e + 1) * per], axis=1)
         s = N_k > 0
         with lib.DeviceProblem(u, N_k) as p:
             S, sumL, _ = p.streaming_pass(f)
