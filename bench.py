@@ -548,7 +548,8 @@ def e2e_legs(rig, args, prob, K, N_local, N_k):
     res = {}
     for kind in ("pinned", "pageable"):
         if kind == "pageable":
-            if args.e2e_pageable_steps <= 0:
+            # (one pageable + one pinned copy of the shard per rank: bounded to 4 ranks' worth of host memory)
+            if args.e2e_pageable_steps <= 0 or rig.world > 4:
                 continue
             src = np.empty((K, N_local))
             src[:] = pin.array
