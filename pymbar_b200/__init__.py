@@ -94,9 +94,24 @@ def trim():
     _lib.check(_lib.load().mbar_b200_trim())
 
 
+def _autoinstall():
+    """PYMBAR_B200=1 in the environment: `import pymbar_b200` alone routes pymbar through the B200 backend (the
+    switch SURVEY.md section 5 asks for, in the style of PYMBAR_DISABLE_JAX)."""
+    import os
+
+    if os.environ.get("PYMBAR_B200", "").lower() in ("1", "true", "yes"):
+        try:
+            install()
+        except ImportError:          # pymbar itself not importable here: nothing to route
+            pass
+
+
 def __getattr__(name):
     if name == "mbar_solvers":
         import importlib
 
         return importlib.import_module(".mbar_solvers", __name__)
     raise AttributeError(name)
+
+
+_autoinstall()

@@ -66,3 +66,19 @@ def test_installed_backend_serves_an_mbar_like_caller():
     finally:
         pymbar_b200.uninstall()
         pymbar_b200.mbar_solvers.clear_cache()
+
+
+def test_environment_switch_installs_at_import():
+    """PYMBAR_B200=1: importing pymbar_b200 alone rebinds pymbar.mbar_solvers."""
+    if not os.path.isdir("/root/reference/pymbar"):
+        pytest.skip("reference checkout not present on this box")
+    import subprocess
+
+    env = dict(os.environ, PYMBAR_B200="1", PYMBAR_DISABLE_JAX="1",
+               PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "oracle", "ref_shim"), "/root/reference"]))
+    code = ("import pymbar_b200, pymbar.mbar_solvers as m, pymbar.mbar as mb; "
+            "from pymbar_b200 import mbar_solvers as o; "
+            "assert m.solve_mbar_for_all_states is o.solve_mbar_for_all_states; "
+            "assert isinstance(mb.MBAR.__dict__['Log_W_nk'], property); print('SWITCH_OK')")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert "SWITCH_OK" in out.stdout, out.stdout + out.stderr[-2000:]
