@@ -451,6 +451,36 @@ def hessian_roofline(prob, K, N_local, fp64_peak, plain_pass_ms=None):
             "how": "CUDA events inside the library around weights_kernel and hessian kernel + reduction, median of 3"}
 
 
+def run_c1(rig, args):
+    """C1 (BASELINE.json configs[0]): testsystems.HarmonicOscillatorsTestCase defaults, K=5, N=5000 — the
+    reference's own CPU-runnable case.  CPU leg: the numpy oracle port of the reference solve (this is the
+    cpu_baseline of that config); GPU leg: the mirror's solve_mbar_for_all_states on the same host array, upload
+    included, and |delta f| between the two."""
+    from oracle import mbar_oracle as orc
+    from oracle import testsystems as ots
+    from pymbar_b200 import mbar_solvers as ms
+
+    O, Kk, Nk = [0.0, 1.0, 2.0, 3.0, 4.0], [1.0, 2.0, 4.0, 8.0, 16.0], [1000] * 5
+    _, u_kn, N_k = ots.harmonic_u_kn(O, Kk, Nk, seed=0)
+    t0 = time.perf_counter()
+    f_cpu = orc.mbar_f_k(u_kn, N_k)
+    t_cpu = time.perf_counter() - t0
+    sws = np.arange(5)
+    ms._DEVICE = rig.local
+    times = []
+    for _ in range(4):
+        proto = tuple({k: (dict(v) if isinstance(v, dict) else v) for k, v in st.items()}
+                      for st in ms.DEFAULT_SOLVER_PROTOCOL)
+        t0 = time.perf_counter()
+        f_gpu = ms.solve_mbar_for_all_states(u_kn, np.asarray(N_k), np.zeros(5), sws, proto)
+        times.append(time.perf_counter() - t0)
+    ms.clear_cache()
+    return {"workload": "C1: HarmonicOscillatorsTestCase defaults, K=5, N=5000, default solver protocol", "K": 5,
+            "N": 5000, "reference_cpu_solve_s": t_cpu, "gpu_solve_s_first": times[0], "gpu_solve_s": float(np.median(times[1:])),
+            "max_abs_df_vs_cpu": float(np.max(np.abs(f_gpu - f_cpu))),
+            "note": "plumbing config: both legs are dominated by Python/scipy overhead (hybr with device closures)"}
+
+
 def run_c2(rig, args):
     """C2: synthetic u_kn N=1e6, K=64, adaptive solver fp64 on one B200 (every rank runs its own copy)."""
     K, N = 64, 1_000_000
@@ -651,7 +681,7 @@ def run_ours(args):
     distributed = rig.distributed
 
     if args.config != "c3":
-        out = {"c2": run_c2, "c4": run_c4, "c5": run_c5}[args.config](rig, args)
+        out = {"c1": run_c1, "c2": run_c2, "c4": run_c4, "c5": run_c5}[args.config](rig, args)
         if rank == 0:
             print(json.dumps({"metric": METRIC, "config_line": args.config, "n_gpus": world, "dtype": "f64",
                               "data": "synthetic", "config": out}), flush=True)
@@ -748,7 +778,7 @@ def run_ours(args):
     # ---- the other BASELINE configs, briefly (full detail: --config c2|c4|c5) ---------------------------
     configs = {}
     if args.extra_configs:
-        for name, fn in (("c2", run_c2), ("c4", run_c4), ("c5", run_c5)):
+        for name, fn in (("c1", run_c1), ("c2", run_c2), ("c4", run_c4), ("c5", run_c5)):
             try:
                 configs[name] = fn(rig, args)
             except Exception as exc:  # pragma: no cover
@@ -810,7 +840,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c3", choices=["c2", "c3", "c4", "c5"],
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5"],
                     help="c3 (default) = BASELINE metric line with the other configs summarised under `configs`; "
                          "c2 / c4 / c5 = that BASELINE.json config alone, in detail")
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU)
