@@ -589,7 +589,12 @@ static void key_push(std::vector<uint64_t>& key, const FusedParams& p) {
 static int run_adaptive_batch(mbar_b200_ctx* c, const FusedParams& pF, const FusedParams& pS, const FusedParams& pN,
                               const FusedParams* pM, int batch) {
     static const bool noGraph = std::getenv("MBAR_B200_NO_GRAPH") != nullptr;
-    if (noGraph || !c->graphWarm) {
+    // Sharded problems keep the kernel-by-kernel path: an iteration then contains NCCL collectives (K x K
+    // second moments; every pass without peer inboxes), and the 2-rank run with captured collectives did not
+    // complete on the 8-GPU box this round (the same build without capture passed at 2 and 4 ranks), so the
+    // graph is restricted to what has been verified: one GPU.  MBAR_B200_GRAPH_MULTI=1 re-enables it.
+    static const bool graphMulti = std::getenv("MBAR_B200_GRAPH_MULTI") != nullptr;
+    if (noGraph || !c->graphWarm || (c->nranks > 1 && !graphMulti)) {
         for (int b = 0; b < batch; ++b) MBAR_TRY(enqueue_adaptive_iteration(c, pF, pS, pN, pM));
         c->graphWarm = true;
         return MBAR_B200_OK;
