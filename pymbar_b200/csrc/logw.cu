@@ -62,24 +62,14 @@ int launch_logw(mbar_b200_ctx* ctx, const double* h_f, double* logW_host, int64_
         pinnedDst = (attr.type == cudaMemoryTypeHost);
     else
         cudaGetLastError();
+#if defined(MADV_HUGEPAGE)
     if (!pinnedDst) {
-        // A freshly allocated destination (np.empty) is faulted in page by page while it is filled, under the
-        // address-space lock: pre-populate it from the worker pool (MADV_POPULATE_WRITE, Linux >= 5.14; silently
-        // skipped where the kernel does not know it) so that the drain threads copy at memory speed.
+        // a freshly allocated destination is faulted in page by page while it is filled: ask for huge pages
         const uintptr_t a0 = (reinterpret_cast<uintptr_t>(logW_host) + 4095) & ~(uintptr_t)4095;
         const uintptr_t a1 = (reinterpret_cast<uintptr_t>(logW_host + (n - 1) * ld + K)) & ~(uintptr_t)4095;
-        if (a1 > a0 + (64u << 20)) {
-#if defined(MADV_HUGEPAGE)
-            madvise(reinterpret_cast<void*>(a0), a1 - a0, MADV_HUGEPAGE);
-#endif
-            const uintptr_t piece = 32u << 20;
-            const int nPieces = (int)((a1 - a0 + piece - 1) / piece);
-            host_parallel(nPieces, [&](int i) {
-                const uintptr_t b0 = a0 + (uintptr_t)i * piece, b1 = std::min(a1, b0 + piece);
-                madvise(reinterpret_cast<void*>(b0), b1 - b0, 23 /* MADV_POPULATE_WRITE */);
-            });
-        }
+        if (a1 > a0 + (8u << 20)) madvise(reinterpret_cast<void*>(a0), a1 - a0, MADV_HUGEPAGE);
     }
+#endif
     const int64_t tileFirst = n0 / TILE_N;
     const int64_t tilesTotal = (n + TILE_N - 1) / TILE_N;
     int64_t tilesPerChunk = (64ll << 20) / ((int64_t)K * TILE_N * 8);
