@@ -675,10 +675,35 @@ def e2e_legs(rig, args, prob, K, N_local, N_k):
     return e2e, e2e_solve
 
 
+class Watchdog:
+    """Safety net for the driver's unattended runs: the line's core (value, roofline, cpu_baseline) is complete a
+    few seconds after the timed loop; everything after it is supporting evidence.  If those sections have not
+    finished by the deadline (a hung collective on one box must not cost the whole measurement), rank 0 prints what
+    it has and every rank exits 0.  Never fires in a healthy run (N=1: ~70 s, N=8: ~200 s)."""
+
+    def __init__(self, rank, deadline_s):
+        self.rank, self.line, self.stage = rank, None, "setup"
+        self.timer = threading.Timer(deadline_s, self.fire)
+        self.timer.daemon = True
+        self.timer.start()
+        self.deadline_s = deadline_s
+
+    def fire(self):
+        if self.rank == 0 and self.line is not None:
+            self.line["watchdog"] = (f"sections after the timed measurement did not finish within {self.deadline_s:.0f} s "
+                                     f"(stopped in: {self.stage}); core fields are complete")
+            print(json.dumps(self.line), flush=True)
+        os._exit(0 if (self.line is not None or self.rank != 0) else 3)
+
+    def cancel(self):
+        self.timer.cancel()
+
+
 def run_ours(args):
     rig = Rig()
     world, rank, local = rig.world, rig.rank, rig.local
     distributed = rig.distributed
+    dog = Watchdog(rank, float(os.environ.get("BENCH_DEADLINE_S", "480")))
 
     if args.config != "c3":
         out = {"c1": run_c1, "c2": run_c2, "c4": run_c4, "c5": run_c5}[args.config](rig, args)
@@ -729,62 +754,7 @@ def run_ours(args):
     ceil_ms = rig.max_over_ranks([prob.last_loop_ms()["kernel_ms_sum"] / 20])[0]
     stream_ceiling = 8.0 * K * N_local / (ceil_ms * 1e-3) / 1e9
 
-    # multi-rank parity, visible to the driver (N > 1)
-    parity_mr = multi_rank_parity(rig, prob, f, K) if distributed else None
-
-    # the Newton half of C3: Hessian roofline + adaptive solve (device-resident vs host-stepped), not timed above
-    fp64_peak = measure_fp64_peak(local)
-    roof_h = hessian_roofline(prob, K, N_local, fp64_peak, kern_ms_per_launch) if not distributed else None
-    rig.barrier()
-    if not distributed:
-        adaptive_c3, f_solved = adaptive_report(prob, K, "C3 K=256 N=1e7", maxiter=100)
-        adaptive_solve = dict(adaptive_c3["device"])
-        adaptive_solve["stepped_device_ms"] = adaptive_c3["stepped"]["device_ms"]
-        adaptive_solve["kernels"] = adaptive_c3["kernels"]
-        adaptive_solve["hessian_ms"] = adaptive_c3["hessian_ms"]
-    else:
-        t0 = time.perf_counter()
-        f_solved, info = prob.solve_adaptive(np.zeros(K), tol=1e-12, maxiter=100, min_sc_iter=0)
-        adaptive_solve = {k: info[k] for k in ("success", "iterations", "nr_iterations", "sci_iterations", "passes",
-                                               "hessian_passes", "gnorm", "device_ms")}
-        adaptive_solve["wall_s"] = time.perf_counter() - t0
-
-    # parity spot check of the timed state against the CPU oracle on a slice (not timed)
-    parity = None
-    if rank == 0:
-        from oracle import mbar_oracle as orc
-        from pymbar_b200 import DeviceProblem
-
-        sl = prob.download(0, 4096)
-        try:
-            p2 = DeviceProblem(sl, N_k, device=local)
-            Sdev, _, _ = p2.streaming_pass(f)
-            S_ref, _ = orc.single_pass_sums(sl, N_k, f)
-            parity = float(np.max(np.abs(Sdev - S_ref) / S_ref))
-            p2.close()
-        except Exception as exc:  # pragma: no cover
-            parity = f"failed: {exc}"
-
-    # ---- e2e legs (close the resident problem first) ---------------------------------------------------
-    e2e, e2e_solve = (None, None)
-    if args.e2e_steps > 0:
-        e2e, e2e_solve = e2e_legs(rig, args, prob, K, N_local, N_k)
-    else:
-        prob.close()
-    import pymbar_b200
-
-    pymbar_b200.trim()
-
-    # ---- the other BASELINE configs, briefly (full detail: --config c2|c4|c5) ---------------------------
-    configs = {}
-    if args.extra_configs:
-        for name, fn in (("c1", run_c1), ("c2", run_c2), ("c4", run_c4), ("c5", run_c5)):
-            try:
-                configs[name] = fn(rig, args)
-            except Exception as exc:  # pragma: no cover
-                configs[name] = {"failed": repr(exc)[:300]}
-            pymbar_b200.trim()
-
+    line = None
     if rank == 0:
         cpu_val, cpu_step, n_sample = time_cpu_reference(K, budget_s=args.cpu_budget, steps=2, warmup=1)
         traffic = ncu_traffic(K, N_local)
@@ -815,22 +785,97 @@ def run_ours(args):
                          "stream_ceiling_how": "same kernel with the arithmetic skipped (MBAR_B200_FUSED_SKIP=1): "
                                                "cp.async.bulk ring + mbarriers only, 20 launches, CUDA events",
                          "how": "per-launch cudaEvent pairs recorded around the kernel inside the timed loop"},
-            "roofline_hessian": roof_h,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": "port",
                              "host_cpus": os.cpu_count(),
                              "c_port_all_threads": time_c_port(K),
                              "sample": f"numpy oracle self_consistent_update on K={K}, N={n_sample} of the same "
                                        f"family ({cpu_step:.2f} s/step); reference is single-threaded numpy"},
-            "e2e": e2e,
-            "e2e_solve": e2e_solve,
-            "adaptive_solve": adaptive_solve,
             "gpu_launches": c1["launches"] - c0["launches"],
             "clocks": clocks,
-            "parity_S_rel_err_vs_oracle_slice": parity,
-            "parity_multi_rank": parity_mr,
-            "configs": configs,
         }
-        print(json.dumps(line), flush=True)
+    dog.line = line
+    dog.stage = "parity_multi_rank"
+    # multi-rank parity, visible to the driver (N > 1)
+    parity_mr = multi_rank_parity(rig, prob, f, K) if distributed else None
+    if line is not None:
+        line["parity_multi_rank"] = parity_mr
+    dog.stage = "roofline_hessian / adaptive_solve"
+
+    # the Newton half of C3: Hessian roofline + adaptive solve (device-resident vs host-stepped), not timed above
+    fp64_peak = measure_fp64_peak(local)
+    roof_h = hessian_roofline(prob, K, N_local, fp64_peak, kern_ms_per_launch) if not distributed else None
+    rig.barrier()
+    if not distributed:
+        adaptive_c3, f_solved = adaptive_report(prob, K, "C3 K=256 N=1e7", maxiter=100)
+        adaptive_solve = dict(adaptive_c3["device"])
+        adaptive_solve["stepped_device_ms"] = adaptive_c3["stepped"]["device_ms"]
+        adaptive_solve["kernels"] = adaptive_c3["kernels"]
+        adaptive_solve["hessian_ms"] = adaptive_c3["hessian_ms"]
+    else:
+        t0 = time.perf_counter()
+        f_solved, info = prob.solve_adaptive(np.zeros(K), tol=1e-12, maxiter=100, min_sc_iter=0)
+        adaptive_solve = {k: info[k] for k in ("success", "iterations", "nr_iterations", "sci_iterations", "passes",
+                                               "hessian_passes", "gnorm", "device_ms")}
+        adaptive_solve["wall_s"] = time.perf_counter() - t0
+
+    if line is not None:
+        line["roofline_hessian"] = roof_h
+        line["adaptive_solve"] = adaptive_solve
+    dog.stage = "parity spot check / e2e"
+    # parity spot check of the timed state against the CPU oracle on a slice (not timed)
+    parity = None
+    if rank == 0:
+        from oracle import mbar_oracle as orc
+        from pymbar_b200 import DeviceProblem
+
+        sl = prob.download(0, 4096)
+        try:
+            p2 = DeviceProblem(sl, N_k, device=local)
+            Sdev, _, _ = p2.streaming_pass(f)
+            S_ref, _ = orc.single_pass_sums(sl, N_k, f)
+            parity = float(np.max(np.abs(Sdev - S_ref) / S_ref))
+            p2.close()
+        except Exception as exc:  # pragma: no cover
+            parity = f"failed: {exc}"
+
+    # ---- e2e legs (close the resident problem first) ---------------------------------------------------
+    if line is not None:
+        line["parity_S_rel_err_vs_oracle_slice"] = parity
+    dog.stage = "e2e"
+    e2e, e2e_solve = (None, None)
+    if args.e2e_steps > 0:
+        e2e, e2e_solve = e2e_legs(rig, args, prob, K, N_local, N_k)
+    else:
+        prob.close()
+    if line is not None:
+        line["e2e"] = e2e
+        line["e2e_solve"] = e2e_solve
+    import pymbar_b200
+
+    pymbar_b200.trim()
+
+    # ---- the other BASELINE configs, briefly (full detail: --config c1|c2|c4|c5) ------------------------
+    configs = {}
+    if line is not None:
+        line["configs"] = configs
+    if args.extra_configs:
+        for name, fn in (("c1", run_c1), ("c2", run_c2), ("c4", run_c4), ("c5", run_c5)):
+            dog.stage = f"configs.{name}"
+            try:
+                configs[name] = fn(rig, args)
+            except Exception as exc:  # pragma: no cover
+                configs[name] = {"failed": repr(exc)[:300]}
+            pymbar_b200.trim()
+
+    dog.stage = "done"
+    dog.cancel()
+    if rank == 0:
+        # key order of the driver contract first, supporting evidence after
+        order = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                 "vs_baseline", "dtype", "data", "iter_per_s", "hbm_gbs_per_gpu", "config", "roofline",
+                 "roofline_hessian", "cpu_baseline", "e2e", "e2e_solve", "adaptive_solve", "gpu_launches", "clocks",
+                 "parity_S_rel_err_vs_oracle_slice", "parity_multi_rank", "configs"]
+        print(json.dumps({k: line.get(k) for k in order}), flush=True)
     rig.close()
 
 
