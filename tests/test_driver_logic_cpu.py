@@ -154,3 +154,56 @@ def test_three_dimensional_input_and_bad_method(patched_pymbar):
     with pytest.raises(patched_pymbar.utils.ParameterError):          # pymbar's own class after install()
         patched_pymbar.MBAR(z["u_kn"], z["N_k"], solver_protocol=({"method": "no-such-method"},))
     del ParameterError
+
+
+def test_facade_lazy_log_weights_and_device_moments(patched_pymbar):
+    """SURVEY 8f N1 / N2 through the real MBAR class (pymbar_b200/facade.py): Log_W_nk is a ticket until somebody
+    reads it; N_eff, overlap and dDelta_f come from the K x K moments; every number equals what the unmodified
+    reference produced for the fixture (oracle/make_golden.py)."""
+    from pymbar_b200 import facade
+
+    z = _cases.load("small_osc_8x40")
+    s0 = dict(facade.STATS)
+    m = patched_pymbar.MBAR(z["u_kn"], z["N_k"])
+    assert facade.STATS["tickets"] == s0["tickets"] + 1 and facade.STATS["redeemed"] == s0["redeemed"]
+    assert isinstance(m.__dict__["_b200_logw"], facade.LogWeightTicket)          # nothing downloaded yet
+    r = m.compute_free_energy_differences(return_theta=True)
+    np.testing.assert_allclose(r["Delta_f"], z["est_Delta_f"], atol=1e-9)
+    np.testing.assert_allclose(r["dDelta_f"], z["est_dDelta_f"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(r["Theta"], z["est_Theta"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(m.compute_effective_sample_number(), z["est_N_eff"], rtol=1e-8)
+    ov = m.compute_overlap()
+    np.testing.assert_allclose(ov["matrix"], z["est_overlap_matrix"], rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(np.real(ov["scalar"]), z["est_overlap_scalar"], rtol=1e-7)
+    assert facade.STATS["redeemed"] == s0["redeemed"] and facade.STATS["moments"] == s0["moments"] + 1
+    # expectations / perturbed free energies: the routine behind them is served by the augmented problem
+    x = z["x_n"]
+    e = m.compute_expectations(x.copy())
+    np.testing.assert_allclose(e["mu"], z["expt_avg_mu"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(e["sigma"], z["expt_avg_sigma"], rtol=1e-5, atol=1e-9)
+    pf = m.compute_perturbed_free_energies(z["pert_u_ln"].copy())
+    np.testing.assert_allclose(pf["Delta_f"], z["pert_Delta_f"], atol=1e-8)
+    np.testing.assert_allclose(pf["dDelta_f"], z["pert_dDelta_f"], rtol=1e-5, atol=1e-9)
+    assert facade.STATS["redeemed"] == s0["redeemed"] and facade.STATS["expectations"] >= s0["expectations"] + 2
+    # the first read downloads the matrix: a plain writable ndarray, as in the reference
+    lw = m.Log_W_nk
+    assert isinstance(lw, np.ndarray) and lw.flags.writeable and lw.shape == (z["u_kn"].shape[1], z["u_kn"].shape[0])
+    assert facade.STATS["redeemed"] == s0["redeemed"] + 1
+    np.testing.assert_allclose(np.exp(lw) @ z["N_k"], 1.0, atol=1e-9)
+    assert m.Log_W_nk is lw                                                        # cached after the first read
+    # uncertainty methods outside the device path fall through to the original implementation
+    r_svd = m.compute_free_energy_differences(uncertainty_method="svd")
+    np.testing.assert_allclose(r_svd["dDelta_f"], r["dDelta_f"], rtol=1e-6, atol=1e-9)
+
+
+def test_facade_bar_initialisation_and_uninstall(patched_pymbar):
+    import pymbar_b200
+
+    z = _cases.load("small_empty_state")
+    m = patched_pymbar.MBAR(z["u_kn"], z["N_k"], initialize="BAR")
+    assert np.max(np.abs(m.f_k - z["fk_default"])) < 1e-8                          # the start only seeds the solver
+    cls = patched_pymbar.mbar.MBAR
+    assert isinstance(cls.__dict__["Log_W_nk"], property)
+    pymbar_b200.uninstall()
+    assert "Log_W_nk" not in cls.__dict__ and cls.compute_overlap.__module__ == "pymbar.mbar"
+    pymbar_b200.install()                                                          # (the fixture uninstalls again)
