@@ -10,7 +10,7 @@ import sys
 
 import numpy as np
 
-__version__ = "0.0-stub"
+__version__ = "2.10.2"   # (pandas probes the version of an installed numexpr; any valid PEP 440 string)
 
 
 def evaluate(expr, local_dict=None, global_dict=None, **_kw):
