@@ -145,3 +145,21 @@ def test_default_line_has_every_key_the_driver_reads(monkeypatch, world):
 def test_single_config_lines(monkeypatch, cfg):
     d = _run(monkeypatch, ["--config", cfg], 1)
     assert d["config_line"] == cfg and d["config"]["workload"].startswith(cfg.upper())
+
+
+def test_watchdog_prints_the_core_line_and_exits_zero():
+    """A supporting section that never returns must not cost the measurement: after the deadline rank 0 prints the
+    core line (with a `watchdog` note) and the process exits 0; ranks without a line exit 0 silently."""
+    import subprocess
+
+    code = ("import sys, time; sys.path.insert(0, %r); import bench; "
+            "d = bench.Watchdog(int(sys.argv[1]), 0.4); "
+            "d.line = {'metric': 'm', 'value': 1.0} if sys.argv[2] == 'line' else None; d.stage = 'e2e'; time.sleep(30)" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code, "0", "line"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["value"] == 1.0 and "e2e" in d["watchdog"]
+    out = subprocess.run([sys.executable, "-c", code, "3", "noline"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+    out = subprocess.run([sys.executable, "-c", code, "0", "noline"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 3          # rank 0 with nothing measured: a failure, not a silent success
